@@ -1,0 +1,110 @@
+"""ctypes binding of the C-ABI in include/armsim.h (libarmsim.so).
+
+This is the ONLY compute path of the package: if the CUDA library is missing or no CUDA device is usable the
+calls raise -- there is no CPU or PyTorch fallback (and nothing here touches oracle/).
+"""
+import ctypes as C
+import os
+
+from . import _build
+
+NJ = 7
+TASK_REACH, TASK_PUSH, TASK_PICK, TASK_KUKA_REACH = 0, 1, 2, 3
+ROBOT_KUKA_IIWA, ROBOT_DIANA_S1, ROBOT_CUSTOM = 0, 1, 2
+MODE_IK_TELEPORT, MODE_TORQUE = 0, 1
+MAP_AUTO, MAP_LANE, MAP_WARP = 0, 1, 2
+(F_Q, F_QD, F_GOAL, F_STEP, F_EPISODE, F_CUBE_POS, F_CUBE_QUAT, F_CUBE_LINVEL, F_CUBE_ANGVEL, F_LAST_DIST, F_GRIP,
+ F_IK_ITERS) = range(12)
+FIELD_WIDTH = {F_Q: 7, F_QD: 7, F_GOAL: 3, F_STEP: 1, F_EPISODE: 1, F_CUBE_POS: 3, F_CUBE_QUAT: 4, F_CUBE_LINVEL: 3,
+               F_CUBE_ANGVEL: 3, F_LAST_DIST: 1, F_GRIP: 1, F_IK_ITERS: 1}
+INT_FIELDS = (F_STEP, F_EPISODE, F_IK_ITERS)
+
+EXPORTS = [
+    "armsim_abi_version", "armsim_last_error", "armsim_default_config", "armsim_create", "armsim_destroy",
+    "armsim_reset", "armsim_step", "armsim_step_host", "armsim_reset_host", "armsim_set_state", "armsim_get_state",
+    "armsim_obs_dim", "armsim_action_dim", "armsim_n_envs", "armsim_mapping", "armsim_launch_count", "armsim_fk_host",
+]
+
+
+class ArmsimChain(C.Structure):
+    _fields_ = [("base_xyz", C.c_double * 3), ("base_rpy", C.c_double * 3),
+                ("xyz", (C.c_double * 3) * NJ), ("rpy", (C.c_double * 3) * NJ),
+                ("lower", C.c_double * NJ), ("upper", C.c_double * NJ), ("effort", C.c_double * NJ),
+                ("velocity", C.c_double * NJ), ("damping", C.c_double * NJ),
+                ("mass", C.c_double * NJ), ("com", (C.c_double * 3) * NJ), ("inertia", (C.c_double * 6) * NJ)]
+
+
+class ArmsimConfig(C.Structure):
+    """include/armsim.h ArmsimConfig."""
+    _fields_ = [("struct_size", C.c_int32), ("task", C.c_int32), ("robot", C.c_int32), ("mode", C.c_int32),
+                ("mapping", C.c_int32), ("n_envs", C.c_int32), ("device", C.c_int32), ("auto_reset", C.c_int32),
+                ("seed", C.c_uint64), ("env_id_offset", C.c_uint64),
+                ("dv", C.c_double), ("reach_dis", C.c_double), ("max_steps", C.c_int32),
+                ("ws_lo", C.c_double * 3), ("ws_hi", C.c_double * 3),
+                ("goal_lo", C.c_double * 3), ("goal_hi", C.c_double * 3),
+                ("target_rpy", C.c_double * 3), ("init_q", C.c_double * NJ),
+                ("ik_damping", C.c_double), ("ik_max_iters", C.c_int32), ("ik_residual", C.c_double),
+                ("clamp_joint_limits", C.c_int32), ("reserved", C.c_int32 * 7),
+                ("custom_chain", C.POINTER(ArmsimChain))]
+
+
+class ArmsimError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libarmsim.so (building it first if the sources are newer).  Raises when it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build_libarmsim()
+    try:
+        L = C.CDLL(path)
+    except OSError as e:  # loud: no fallback
+        raise ArmsimError("cannot load %s: %s (the package has no CPU fallback)" % (path, e)) from e
+    vp, i32 = C.c_void_p, C.c_int32
+    L.armsim_abi_version.restype = i32
+    L.armsim_last_error.restype = C.c_char_p
+    L.armsim_default_config.argtypes = [i32, C.POINTER(ArmsimConfig)]
+    L.armsim_create.argtypes = [C.POINTER(ArmsimConfig), C.POINTER(vp)]
+    L.armsim_destroy.argtypes = [vp]
+    L.armsim_destroy.restype = None
+    L.armsim_reset.argtypes = [vp, vp, vp, vp]
+    L.armsim_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.armsim_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.armsim_reset_host.argtypes = [vp, vp, vp]
+    L.armsim_set_state.argtypes = [vp, i32, vp, C.c_size_t]
+    L.armsim_get_state.argtypes = [vp, i32, vp, C.c_size_t]
+    for f in ("armsim_obs_dim", "armsim_action_dim", "armsim_n_envs", "armsim_mapping"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = i32
+    L.armsim_launch_count.argtypes = [vp]
+    L.armsim_launch_count.restype = C.c_int64
+    L.armsim_fk_host.argtypes = [vp, vp, i32, vp, vp]
+    if L.armsim_abi_version() != 1:
+        raise ArmsimError("libarmsim ABI version %d != 1" % L.armsim_abi_version())
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise ArmsimError("libarmsim error %d: %s" % (rc, lib().armsim_last_error().decode()))
+
+
+def default_config(task, **overrides):
+    cfg = ArmsimConfig()
+    check(lib().armsim_default_config(task, C.byref(cfg)))
+    for k, v in overrides.items():
+        cur = getattr(cfg, k)
+        if hasattr(cur, "__len__"):
+            for i, x in enumerate(v):
+                cur[i] = x
+        else:
+            setattr(cfg, k, v)
+    return cfg

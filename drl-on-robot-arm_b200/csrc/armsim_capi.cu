@@ -1,0 +1,363 @@
+// armsim_capi.cu -- the C-ABI of include/armsim.h on top of the sm_100a kernels.
+// No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "armsim.h"
+#include "armsim_defaults.h"
+#include "armsim_kernels.cuh"
+#include "armsim_robot_models.h"
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return fail(ARMSIM_E_CUDA, "%s: %s", #call, cudaGetErrorString(_e));    \
+  } while (0)
+
+struct ArmSim {
+  ArmsimConfig cfg;
+  int n = 0, obs_dim = 0, act_dim = 3, mapping = ARMSIM_MAP_LANE;
+  ChainParams chain;
+  TaskParams task;
+  StatePtrs S{};
+  void* state_block = nullptr;   // one allocation holding every SoA field
+  // *_host path: one pinned block + one device block, outputs contiguous so the D2H is a single copy
+  char* h_pin = nullptr;
+  char* d_io = nullptr;
+  size_t off_obs = 0, off_reward = 0, off_done = 0, off_success = 0, out_bytes = 0, act_bytes = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+};
+
+static void rpy_to_mat(const double rpy[3], double R[9]) {
+  const double cr = cos(rpy[0]), sr = sin(rpy[0]), cp = cos(rpy[1]), sp = sin(rpy[1]), cy = cos(rpy[2]), sy = sin(rpy[2]);
+  R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
+  R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
+  R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
+}
+
+template <class Model>
+static void fill_chain(const Model& m, ChainParams& c) {
+  double R[9];
+  rpy_to_mat(m.base_rpy, R);
+  for (int i = 0; i < 9; ++i) c.Rb[i] = (float)R[i];
+  for (int i = 0; i < 3; ++i) c.tb[i] = (float)m.base_xyz[i];
+  for (int j = 0; j < NJ; ++j) {
+    rpy_to_mat(m.rpy[j], R);
+    for (int i = 0; i < 9; ++i) c.Rf[j][i] = (float)R[i];
+    for (int i = 0; i < 3; ++i) c.t[j][i] = (float)m.xyz[j][i];
+    c.lower[j] = (float)m.lower[j];
+    c.upper[j] = (float)m.upper[j];
+  }
+}
+
+static void quat_from_euler(const double rpy[3], float q[4]) {
+  const double hr = rpy[0] * 0.5, hp = rpy[1] * 0.5, hy = rpy[2] * 0.5;
+  const double cr = cos(hr), sr = sin(hr), cp = cos(hp), sp = sin(hp), cy = cos(hy), sy = sin(hy);
+  q[0] = (float)(sr * cp * cy - cr * sp * sy);
+  q[1] = (float)(cr * sp * cy + sr * cp * sy);
+  q[2] = (float)(cr * cp * sy - sr * sp * cy);
+  q[3] = (float)(cr * cp * cy + sr * sp * sy);
+}
+
+static int field_width(int32_t f) {
+  switch (f) {
+    case ARMSIM_F_Q: case ARMSIM_F_QD: return 7;
+    case ARMSIM_F_GOAL: case ARMSIM_F_CUBE_POS: case ARMSIM_F_CUBE_LINVEL: case ARMSIM_F_CUBE_ANGVEL: return 3;
+    case ARMSIM_F_CUBE_QUAT: return 4;
+    case ARMSIM_F_STEP: case ARMSIM_F_EPISODE: case ARMSIM_F_LAST_DIST: case ARMSIM_F_GRIP: case ARMSIM_F_IK_ITERS: return 1;
+    default: return -1;
+  }
+}
+
+static void* field_ptr(ArmSim* s, int32_t f) {
+  const size_t n = (size_t)s->n;
+  switch (f) {
+    case ARMSIM_F_Q: return s->S.q;
+    case ARMSIM_F_QD: return s->S.qd;
+    case ARMSIM_F_GOAL: return s->S.goal;
+    case ARMSIM_F_STEP: return s->S.step;
+    case ARMSIM_F_EPISODE: return s->S.episode;
+    case ARMSIM_F_CUBE_POS: return s->S.cube;
+    case ARMSIM_F_CUBE_QUAT: return s->S.cube + 3 * n;
+    case ARMSIM_F_CUBE_LINVEL: return s->S.cube + 7 * n;
+    case ARMSIM_F_CUBE_ANGVEL: return s->S.cube + 10 * n;
+    case ARMSIM_F_LAST_DIST: return s->S.last_dist;
+    case ARMSIM_F_GRIP: return s->S.grip;
+    case ARMSIM_F_IK_ITERS: return s->S.ik_iters;
+    default: return nullptr;
+  }
+}
+
+extern "C" {
+
+int32_t armsim_abi_version(void) { return ARMSIM_ABI_VERSION; }
+const char* armsim_last_error(void) { return g_err; }
+
+int armsim_default_config(int32_t task, ArmsimConfig* cfg) {
+  int rc = armsim_fill_default_config(task, cfg);
+  if (rc) return fail(rc, "armsim_default_config: bad task %d or null cfg", task);
+  return ARMSIM_OK;
+}
+
+int32_t armsim_obs_dim(const ArmSim* s) { return s ? s->obs_dim : ARMSIM_E_INVALID; }
+int32_t armsim_action_dim(const ArmSim* s) { return s ? s->act_dim : ARMSIM_E_INVALID; }
+int32_t armsim_n_envs(const ArmSim* s) { return s ? s->n : ARMSIM_E_INVALID; }
+int32_t armsim_mapping(const ArmSim* s) { return s ? s->mapping : ARMSIM_E_INVALID; }
+int64_t armsim_launch_count(const ArmSim* s) { return s ? s->launches : ARMSIM_E_INVALID; }
+
+void armsim_destroy(ArmSim* s) {
+  if (!s) return;
+  cudaSetDevice(s->cfg.device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->state_block) cudaFree(s->state_block);
+  if (s->d_io) cudaFree(s->d_io);
+  if (s->h_pin) cudaFreeHost(s->h_pin);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cudaStream_t st) {
+  const int grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
+  switch (s->cfg.task) {
+    case ARMSIM_TASK_REACH: reset_lane_kernel<ARMSIM_TASK_REACH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
+    case ARMSIM_TASK_PUSH: reset_lane_kernel<ARMSIM_TASK_PUSH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
+    case ARMSIM_TASK_PICK: reset_lane_kernel<ARMSIM_TASK_PICK><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
+    case ARMSIM_TASK_KUKA_REACH: reset_lane_kernel<ARMSIM_TASK_KUKA_REACH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
+    default: return fail(ARMSIM_E_INVALID, "bad task");
+  }
+  s->launches += 1;
+  CU(cudaGetLastError());
+  return ARMSIM_OK;
+}
+
+static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st) {
+  const int grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
+  switch (s->cfg.task) {
+    case ARMSIM_TASK_REACH: step_lane_kernel<ARMSIM_TASK_REACH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su); break;
+    case ARMSIM_TASK_PUSH: step_lane_kernel<ARMSIM_TASK_PUSH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su); break;
+    case ARMSIM_TASK_PICK: step_lane_kernel<ARMSIM_TASK_PICK><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su); break;
+    case ARMSIM_TASK_KUKA_REACH: step_lane_kernel<ARMSIM_TASK_KUKA_REACH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su); break;
+    default: return fail(ARMSIM_E_INVALID, "bad task");
+  }
+  s->launches += 1;
+  CU(cudaGetLastError());
+  return ARMSIM_OK;
+}
+
+int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
+  if (!cfg || !out) return fail(ARMSIM_E_INVALID, "armsim_create: null argument");
+  *out = nullptr;
+  if (cfg->struct_size != (int32_t)sizeof(ArmsimConfig))
+    return fail(ARMSIM_E_INVALID, "armsim_create: struct_size %d != %zu (ABI mismatch)", cfg->struct_size, sizeof(ArmsimConfig));
+  if (cfg->n_envs <= 0) return fail(ARMSIM_E_INVALID, "armsim_create: n_envs must be > 0");
+  if (cfg->task < 0 || cfg->task > ARMSIM_TASK_KUKA_REACH) return fail(ARMSIM_E_INVALID, "armsim_create: bad task %d", cfg->task);
+  if (cfg->mode != ARMSIM_MODE_IK_TELEPORT) return fail(ARMSIM_E_INVALID, "armsim_create: mode %d not available in this build", cfg->mode);
+  if (cfg->ik_max_iters < 0 || cfg->max_steps < 0) return fail(ARMSIM_E_INVALID, "armsim_create: negative iteration / step limit");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(ARMSIM_E_CUDA, "armsim_create: no usable CUDA device (%s); libarmsim has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(ARMSIM_E_INVALID, "armsim_create: device %d out of range [0,%d)", cfg->device, ndev);
+  CU(cudaSetDevice(cfg->device));
+
+  ArmSim* s = new (std::nothrow) ArmSim();
+  if (!s) return fail(ARMSIM_E_NOMEM, "armsim_create: host allocation failed");
+  s->cfg = *cfg;
+  s->cfg.custom_chain = nullptr;
+  s->n = cfg->n_envs;
+  if (cfg->robot == ARMSIM_ROBOT_KUKA_IIWA) fill_chain(ARMSIM_MODEL_KUKA_IIWA, s->chain);
+  else if (cfg->robot == ARMSIM_ROBOT_DIANA_S1) fill_chain(ARMSIM_MODEL_DIANA_S1, s->chain);
+  else if (cfg->robot == ARMSIM_ROBOT_CUSTOM && cfg->custom_chain) fill_chain(*cfg->custom_chain, s->chain);
+  else { delete s; return fail(ARMSIM_E_INVALID, "armsim_create: bad robot %d (custom needs custom_chain)", cfg->robot); }
+
+  TaskParams& T = s->task;
+  memset(&T, 0, sizeof(T));
+  T.task = cfg->task; T.n = s->n; T.max_steps = cfg->max_steps; T.auto_reset = cfg->auto_reset ? 1 : 0;
+  T.ik_max_iters = cfg->ik_max_iters; T.napply = cfg->task == ARMSIM_TASK_PICK ? 6 : NJ;
+  T.clamp = cfg->clamp_joint_limits ? 1 : 0;
+  T.obs_dim = s->obs_dim = cfg->task == ARMSIM_TASK_REACH ? 6 : (cfg->task == ARMSIM_TASK_KUKA_REACH ? 3 : 9);
+  T.dv = (float)cfg->dv; T.reach_dis = (float)cfg->reach_dis; T.ik_damping = (float)cfg->ik_damping; T.ik_residual = (float)cfg->ik_residual;
+  for (int i = 0; i < 3; ++i) {
+    T.ws_lo[i] = (float)cfg->ws_lo[i]; T.ws_hi[i] = (float)cfg->ws_hi[i];
+    T.goal_lo[i] = (float)cfg->goal_lo[i]; T.goal_span[i] = (float)(cfg->goal_hi[i] - cfg->goal_lo[i]);
+  }
+  quat_from_euler(cfg->target_rpy, T.tquat);
+  for (int j = 0; j < NJ; ++j) T.init_q[j] = (float)cfg->init_q[j];
+  T.seed_lo = (uint32_t)cfg->seed; T.seed_hi = (uint32_t)(cfg->seed >> 32);
+  T.gid_offset = cfg->env_id_offset;
+  s->mapping = ARMSIM_MAP_LANE;
+
+  // state: one block, every field padded to 256 B so each SoA row starts on its own lines
+  const size_t n = (size_t)s->n;
+  auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t sz_q = pad(7 * n * 4), sz_goal = pad(3 * n * 4), sz_i = pad(n * 4), sz_b = pad(n), sz_cube = pad(13 * n * 4);
+  const size_t total = 2 * sz_q + sz_goal + 3 * sz_i + sz_b + sz_cube + 2 * sz_i;
+  if (cudaMalloc(&s->state_block, total) != cudaSuccess) {
+    cudaGetLastError();
+    delete s;
+    return fail(ARMSIM_E_NOMEM, "armsim_create: cudaMalloc of %zu state bytes failed", total);
+  }
+  cudaMemset(s->state_block, 0, total);
+  char* b = (char*)s->state_block;
+  s->S.q = (float*)b; b += sz_q;
+  s->S.qd = (float*)b; b += sz_q;
+  s->S.goal = (float*)b; b += sz_goal;
+  s->S.step = (int*)b; b += sz_i;
+  s->S.episode = (int*)b; b += sz_i;
+  s->S.ik_iters = (int*)b; b += sz_i;
+  s->S.done = (uint8_t*)b; b += sz_b;
+  s->S.cube = (float*)b; b += sz_cube;
+  s->S.last_dist = (float*)b; b += sz_i;
+  s->S.grip = (float*)b; b += sz_i;
+
+  // host-path staging
+  s->act_bytes = pad(n * s->act_dim * 4);
+  s->off_obs = 0;
+  s->off_reward = pad(n * s->obs_dim * 4);
+  s->off_done = s->off_reward + pad(n * 4);
+  s->off_success = s->off_done + pad(n);
+  s->out_bytes = s->off_success + pad(n);
+  if (cudaMalloc((void**)&s->d_io, s->act_bytes + s->out_bytes) != cudaSuccess ||
+      cudaMallocHost((void**)&s->h_pin, s->act_bytes + s->out_bytes) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    armsim_destroy(s);
+    return fail(ARMSIM_E_NOMEM, "armsim_create: staging allocation failed");
+  }
+  int rc = launch_reset(s, nullptr, nullptr, s->stream);
+  if (rc == ARMSIM_OK && cudaStreamSynchronize(s->stream) != cudaSuccess) rc = fail(ARMSIM_E_CUDA, "armsim_create: initial reset failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc != ARMSIM_OK) { armsim_destroy(s); return rc; }
+  *out = s;
+  return ARMSIM_OK;
+}
+
+int armsim_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  if (!s) return fail(ARMSIM_E_INVALID, "armsim_reset: null handle");
+  return launch_reset(s, mask_dev, obs_dev, (cudaStream_t)stream);
+}
+
+int armsim_step(ArmSim* s, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev,
+                void* stream) {
+  if (!s) return fail(ARMSIM_E_INVALID, "armsim_step: null handle");
+  if (!action_dev || !obs_dev || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_step: null buffer");
+  return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream);
+}
+
+int armsim_step_host(ArmSim* s, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                     uint8_t* success_host) {
+  if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_host: null handle");
+  if (!action_host || !obs_host || !reward_host || !done_host || !success_host) return fail(ARMSIM_E_INVALID, "armsim_step_host: null buffer");
+  CU(cudaSetDevice(s->cfg.device));
+  const size_t n = (size_t)s->n;
+  char* h_out = s->h_pin + s->act_bytes;
+  char* d_out = s->d_io + s->act_bytes;
+  memcpy(s->h_pin, action_host, n * s->act_dim * 4);
+  CU(cudaMemcpyAsync(s->d_io, s->h_pin, n * s->act_dim * 4, cudaMemcpyHostToDevice, s->stream));
+  int rc = launch_step(s, (const float*)s->d_io, (float*)(d_out + s->off_obs), (float*)(d_out + s->off_reward),
+                       (uint8_t*)(d_out + s->off_done), (uint8_t*)(d_out + s->off_success), s->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h_out, d_out, s->out_bytes, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  memcpy(obs_host, h_out + s->off_obs, n * s->obs_dim * 4);
+  memcpy(reward_host, h_out + s->off_reward, n * 4);
+  memcpy(done_host, h_out + s->off_done, n);
+  memcpy(success_host, h_out + s->off_success, n);
+  return ARMSIM_OK;
+}
+
+int armsim_reset_host(ArmSim* s, const uint8_t* mask_host, float* obs_host) {
+  if (!s) return fail(ARMSIM_E_INVALID, "armsim_reset_host: null handle");
+  CU(cudaSetDevice(s->cfg.device));
+  const size_t n = (size_t)s->n;
+  char* h_out = s->h_pin + s->act_bytes;
+  char* d_out = s->d_io + s->act_bytes;
+  uint8_t* mask_dev = nullptr;
+  if (mask_host) {  // the done slot of the output block doubles as the mask upload
+    memcpy(h_out + s->off_done, mask_host, n);
+    CU(cudaMemcpyAsync(d_out + s->off_done, h_out + s->off_done, n, cudaMemcpyHostToDevice, s->stream));
+    mask_dev = (uint8_t*)(d_out + s->off_done);
+  }
+  float* obs_dev = (float*)(d_out + s->off_obs);
+  if (mask_host && obs_host) {  // keep rows of un-reset envs as the caller passed them
+    memcpy(h_out + s->off_obs, obs_host, n * s->obs_dim * 4);
+    CU(cudaMemcpyAsync(obs_dev, h_out + s->off_obs, n * s->obs_dim * 4, cudaMemcpyHostToDevice, s->stream));
+  }
+  int rc = launch_reset(s, mask_dev, obs_dev, s->stream);
+  if (rc) return rc;
+  if (obs_host) CU(cudaMemcpyAsync(h_out + s->off_obs, obs_dev, n * s->obs_dim * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (obs_host) memcpy(obs_host, h_out + s->off_obs, n * s->obs_dim * 4);
+  return ARMSIM_OK;
+}
+
+int armsim_set_state(ArmSim* s, int32_t field, const void* host_src, size_t bytes) {
+  if (!s || !host_src) return fail(ARMSIM_E_INVALID, "armsim_set_state: null argument");
+  const int w = field_width(field);
+  if (w < 0 || field == ARMSIM_F_IK_ITERS) return fail(ARMSIM_E_STATE, "armsim_set_state: field %d not writable", field);
+  const size_t n = (size_t)s->n;
+  if (bytes != n * w * 4) return fail(ARMSIM_E_STATE, "armsim_set_state: field %d expects %zu bytes, got %zu", field, n * w * 4, bytes);
+  CU(cudaSetDevice(s->cfg.device));
+  std::vector<uint32_t> soa(n * w);
+  const uint32_t* src = (const uint32_t*)host_src;
+  for (size_t e = 0; e < n; ++e)
+    for (int k = 0; k < w; ++k) soa[(size_t)k * n + e] = src[e * w + k];
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(field_ptr(s, field), soa.data(), bytes, cudaMemcpyHostToDevice));
+  if (field == ARMSIM_F_Q || field == ARMSIM_F_STEP) CU(cudaMemset(s->S.done, 0, n));  // injected envs are live again
+  return ARMSIM_OK;
+}
+
+int armsim_get_state(ArmSim* s, int32_t field, void* host_dst, size_t bytes) {
+  if (!s || !host_dst) return fail(ARMSIM_E_INVALID, "armsim_get_state: null argument");
+  const int w = field_width(field);
+  if (w < 0) return fail(ARMSIM_E_STATE, "armsim_get_state: unknown field %d", field);
+  const size_t n = (size_t)s->n;
+  if (bytes != n * w * 4) return fail(ARMSIM_E_STATE, "armsim_get_state: field %d expects %zu bytes, got %zu", field, n * w * 4, bytes);
+  CU(cudaSetDevice(s->cfg.device));
+  std::vector<uint32_t> soa(n * w);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(soa.data(), field_ptr(s, field), bytes, cudaMemcpyDeviceToHost));
+  uint32_t* dst = (uint32_t*)host_dst;
+  for (size_t e = 0; e < n; ++e)
+    for (int k = 0; k < w; ++k) dst[e * w + k] = soa[(size_t)k * n + e];
+  return ARMSIM_OK;
+}
+
+int armsim_fk_host(ArmSim* s, const float* q_host, int32_t n, float* pos_host, float* rot_host) {
+  if (!s || !q_host || !pos_host || n <= 0) return fail(ARMSIM_E_INVALID, "armsim_fk_host: bad argument");
+  CU(cudaSetDevice(s->cfg.device));
+  float *dq = nullptr, *dp = nullptr, *dr = nullptr;
+  CU(cudaMalloc((void**)&dq, (size_t)n * 7 * 4));
+  CU(cudaMalloc((void**)&dp, (size_t)n * 3 * 4));
+  CU(cudaMalloc((void**)&dr, (size_t)n * 9 * 4));
+  cudaMemcpyAsync(dq, q_host, (size_t)n * 7 * 4, cudaMemcpyHostToDevice, s->stream);
+  fk_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->chain, n, dq, dp, rot_host ? dr : nullptr);
+  s->launches += 1;
+  cudaMemcpyAsync(pos_host, dp, (size_t)n * 3 * 4, cudaMemcpyDeviceToHost, s->stream);
+  if (rot_host) cudaMemcpyAsync(rot_host, dr, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, s->stream);
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  cudaFree(dq); cudaFree(dp); cudaFree(dr);
+  if (e != cudaSuccess) return fail(ARMSIM_E_CUDA, "armsim_fk_host: %s", cudaGetErrorString(e));
+  return ARMSIM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,253 @@
+// armsim_device.cuh -- device-side building blocks of the fused env-step kernels (sm_100a, fp32).
+//
+// Everything here is per-arm scalar math kept entirely in registers; the robot chain and the task constants arrive as
+// __grid_constant__ kernel parameters, i.e. they live in the constant bank and feed FFMA operands directly.
+// Reference behaviour being reproduced: envs/rl_reach_env.py:219-319 (+ push / pick / kuka_reach variants) on top of
+// Bullet's calculateInverseKinematics.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "armsim.h"
+
+#define NJ ARMSIM_NJ
+
+struct ChainParams {
+  float Rb[9], tb[3];        // base transform
+  float Rf[NJ][9];           // fixed rotation of each joint origin (R = Rz(y)Ry(p)Rx(r)), row-major
+  float t[NJ][3];            // joint origin translation in the parent link frame
+  float lower[NJ], upper[NJ];
+};
+
+struct TaskParams {
+  int task, n, max_steps, auto_reset, ik_max_iters, napply, clamp, obs_dim;
+  float dv, reach_dis, ik_damping, ik_residual;
+  float ws_lo[3], ws_hi[3];
+  float goal_lo[3], goal_span[3];
+  float tquat[4];            // IK target orientation, xyzw
+  float init_q[NJ];
+  uint32_t seed_lo, seed_hi;
+  unsigned long long gid_offset;
+};
+
+// per-env state, struct-of-arrays: field k of env e lives at ptr[k * n + e]
+struct StatePtrs {
+  float* q;          // [7][n]
+  float* qd;         // [7][n]   torque mode
+  float* goal;       // [3][n]
+  int* step;         // [n]
+  int* episode;      // [n]
+  int* ik_iters;     // [n]
+  uint8_t* done;     // [n]     latched done flag (auto_reset = 0)
+  float* cube;       // [13][n] pos3 quat4 v3 w3
+  float* last_dist;  // [n]
+  float* grip;       // [n]
+};
+
+// ------------------------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void reset_uniforms(const TaskParams& T, unsigned long long gid, uint32_t episode, uint32_t block,
+                                               float (&u)[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), episode, block, T.seed_lo, T.seed_hi, r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) u[i] = __fmul_rn((float)(r[i] >> 8), 5.9604644775390625e-08f);
+}
+
+// ------------------------------------------------------------------------------------------------ kinematics
+// FK of the 7-joint chain.  P[j] = origin of joint j (world), Z[j] = its axis (world); p, R = EE link frame.
+template <bool WANT_JAC>
+__device__ __forceinline__ void chain_fk(const ChainParams& C, const float (&q)[NJ], float (&p)[3], float (&R)[9],
+                                         float (&P)[NJ][3], float (&Z)[NJ][3]) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = C.Rb[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) p[i] = C.tb[i];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      p[i] = fmaf(R[3 * i + 2], C.t[j][2], fmaf(R[3 * i + 1], C.t[j][1], fmaf(R[3 * i], C.t[j][0], p[i])));
+    float M[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        M[3 * i + k] = fmaf(R[3 * i + 2], C.Rf[j][6 + k], fmaf(R[3 * i + 1], C.Rf[j][3 + k], R[3 * i] * C.Rf[j][k]));
+    if (WANT_JAC) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { P[j][i] = p[i]; Z[j][i] = M[3 * i + 2]; }
+    }
+    float s, c;
+    sincosf(q[j], &s, &c);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      R[3 * i] = fmaf(M[3 * i + 1], s, M[3 * i] * c);
+      R[3 * i + 1] = fmaf(M[3 * i + 1], c, -M[3 * i] * s);
+      R[3 * i + 2] = M[3 * i + 2];
+    }
+  }
+}
+
+// rotation matrix -> unit quaternion (xyzw), Shepperd's method (same branches as btMatrix3x3::getRotation)
+__device__ __forceinline__ void mat_to_quat(const float (&m)[9], float (&q)[4]) {
+  const float tr = m[0] + m[4] + m[8];
+  if (tr > 0.0f) {
+    float s = sqrtf(tr + 1.0f);
+    q[3] = 0.5f * s;
+    s = 0.5f / s;
+    q[0] = (m[7] - m[5]) * s; q[1] = (m[2] - m[6]) * s; q[2] = (m[3] - m[1]) * s;
+  } else if (m[0] >= m[4] && m[0] >= m[8]) {
+    float s = sqrtf(m[0] - m[4] - m[8] + 1.0f);
+    q[0] = 0.5f * s;
+    s = 0.5f / s;
+    q[3] = (m[7] - m[5]) * s; q[1] = (m[3] + m[1]) * s; q[2] = (m[6] + m[2]) * s;
+  } else if (m[4] >= m[8]) {
+    float s = sqrtf(m[4] - m[8] - m[0] + 1.0f);
+    q[1] = 0.5f * s;
+    s = 0.5f / s;
+    q[3] = (m[2] - m[6]) * s; q[2] = (m[7] + m[5]) * s; q[0] = (m[1] + m[3]) * s;
+  } else {
+    float s = sqrtf(m[8] - m[0] - m[4] + 1.0f);
+    q[2] = 0.5f * s;
+    s = 0.5f / s;
+    q[3] = (m[3] - m[1]) * s; q[0] = (m[2] + m[6]) * s; q[1] = (m[5] + m[7]) * s;
+  }
+}
+
+// Orientation error as a rotation vector: angle * axis of (q_target (x) q_cur^-1), angle wrapped to (-pi, pi].
+// Bullet (IKTrajectoryHelper::computeIK) forms it as 2*acos(w) * v/sqrt(1-w^2); for a unit quaternion that is
+// 2*atan2(|v|, w) * v/|v|, which is the form used here because it stays well-conditioned in fp32 when the error is
+// small (acos near 1 loses half the mantissa).
+__device__ __forceinline__ void rot_error(const float (&tq)[4], const float (&R)[9], float (&e)[3]) {
+  float sq[4];
+  mat_to_quat(R, sq);
+  const float ix = -sq[0], iy = -sq[1], iz = -sq[2], iw = sq[3];
+  const float dx = tq[3] * ix + tq[0] * iw + tq[1] * iz - tq[2] * iy;
+  const float dy = tq[3] * iy + tq[1] * iw + tq[2] * ix - tq[0] * iz;
+  const float dz = tq[3] * iz + tq[2] * iw + tq[0] * iy - tq[1] * ix;
+  const float dw = tq[3] * iw - tq[0] * ix - tq[1] * iy - tq[2] * iz;
+  const float vn = sqrtf(dx * dx + dy * dy + dz * dz);
+  float k;
+  if (vn < 1e-4f) {
+    k = dw >= 0.0f ? 2.0f : -2.0f;  // angle ~ 2|v| (or the wrapped equivalent when w < 0)
+  } else {
+    float ang = 2.0f * atan2f(vn, dw);           // [0, 2pi]
+    if (ang > 3.14159265358979f) ang -= 6.28318530717959f;
+    k = ang / vn;
+  }
+  e[0] = k * dx; e[1] = k * dy; e[2] = k * dz;
+}
+
+// One damped-least-squares update  dq = J^T (J J^T + lambda I)^-1 e  -- algebraically identical to Bullet's
+// (J^T J + lambda I)^-1 J^T e (Jacobian::CalcDeltaThetasDLS2) because the reference passes one damping value for all
+// joints (rl_reach_env.py:111-113); the 6x6 form is used because J^T J + 1e-5 I has a null-space eigenvalue of 1e-5
+// next to O(1) ones, which fp32 cannot resolve, while J J^T + 1e-5 I is well conditioned away from singularities.
+__device__ __forceinline__ void dls_update(const float (&p)[3], const float (&P)[NJ][3], const float (&Z)[NJ][3],
+                                           const float (&e)[6], float lambda, float (&dq)[NJ]) {
+  float Jc[NJ][6];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const float r0 = p[0] - P[j][0], r1 = p[1] - P[j][1], r2 = p[2] - P[j][2];
+    Jc[j][0] = Z[j][1] * r2 - Z[j][2] * r1;
+    Jc[j][1] = Z[j][2] * r0 - Z[j][0] * r2;
+    Jc[j][2] = Z[j][0] * r1 - Z[j][1] * r0;
+    Jc[j][3] = Z[j][0]; Jc[j][4] = Z[j][1]; Jc[j][5] = Z[j][2];
+  }
+  // A = J J^T + lambda I (lower triangle)
+  float A[6][6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      float acc = (a == b) ? lambda : 0.0f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc = fmaf(Jc[j][a], Jc[j][b], acc);
+      A[a][b] = acc;
+    }
+  // Cholesky A = L L^T in place, keeping 1/L_ii
+  float inv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int k = 0; k <= i; ++k) {
+      float acc = A[i][k];
+#pragma unroll
+      for (int m = 0; m < k; ++m) acc = fmaf(-A[i][m], A[k][m], acc);
+      if (k == i) {
+        acc = fmaxf(acc, 1e-20f);
+        inv[i] = rsqrtf(acc);
+        A[i][i] = acc * inv[i];
+      } else {
+        A[i][k] = acc * inv[k];
+      }
+    }
+  }
+  float y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float acc = e[i];
+#pragma unroll
+    for (int m = 0; m < i; ++m) acc = fmaf(-A[i][m], y[m], acc);
+    y[i] = acc * inv[i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    float acc = y[i];
+#pragma unroll
+    for (int m = i + 1; m < 6; ++m) acc = fmaf(-A[m][i], y[m], acc);
+    y[i] = acc * inv[i];
+  }
+  float mx = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc = fmaf(Jc[j][a], y[a], acc);
+    dq[j] = acc;
+    mx = fmaxf(mx, fabsf(acc));
+  }
+  const float max_angle = 0.78539816339744831f;  // BussIK MaxAngleDLS = 45 deg
+  if (mx > max_angle) {
+    const float sc = max_angle / mx;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) dq[j] *= sc;
+  }
+}
+
+// calculateInverseKinematics as the reference calls it (rl_reach_env.py:244-250).
+// In/out: q, and the FK state (p, R, P, Z) which must be valid for q on entry and is valid for the returned q.
+__device__ __forceinline__ int ik_solve(const ChainParams& C, const TaskParams& T, const float (&tgt)[3], float (&q)[NJ],
+                                        float (&p)[3], float (&R)[9], float (&P)[NJ][3], float (&Z)[NJ][3]) {
+  int it = 0;
+  float diff = 1e30f;
+  while (it < T.ik_max_iters && diff > T.ik_residual) {
+    float e[6], er[3], dq[NJ];
+    e[0] = tgt[0] - p[0]; e[1] = tgt[1] - p[1]; e[2] = tgt[2] - p[2];
+    rot_error(T.tquat, R, er);
+    e[3] = er[0]; e[4] = er[1]; e[5] = er[2];
+    dls_update(p, P, Z, e, T.ik_damping, dq);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) q[j] += dq[j];
+    chain_fk<true>(C, q, p, R, P, Z);
+    const float d0 = tgt[0] - p[0], d1 = tgt[1] - p[1], d2 = tgt[2] - p[2];
+    diff = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    ++it;
+  }
+  return it;
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }

@@ -1,0 +1,263 @@
+// armsim_kernels.cuh -- the fused Env.step / Env.reset kernels (sm_100a).
+//
+// Mapping "lane": one CUDA lane per arm, state as struct-of-arrays so every state load/store of a warp is one
+// coalesced 128-byte line; the row-major [n,3] actions and [n,obs_dim] observations the caller (PyTorch) wants are
+// staged through shared memory so their global accesses are coalesced too.  One launch = one Env.step for the whole
+// batch: FK -> workspace clip -> DLS IK (<= 20 iterations) -> teleport -> cube / gripper contact step(s) -> reward /
+// done / success -> optional in-kernel auto-reset (Philox) -> obs.
+#pragma once
+#include "armsim_device.cuh"
+#include "cube_model.cuh"
+
+constexpr int LANE_BLOCK = 128;
+
+template <int TASK>
+struct TaskTraits {
+  static constexpr int OBS = (TASK == ARMSIM_TASK_REACH) ? 6 : (TASK == ARMSIM_TASK_KUKA_REACH ? 3 : 9);
+  static constexpr bool HAS_CUBE = (TASK == ARMSIM_TASK_PUSH || TASK == ARMSIM_TASK_PICK);
+};
+
+__device__ __forceinline__ void load_cube(const StatePtrs& S, int n, int e, cube::State& c) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c.pos[i] = S.cube[(0 + i) * n + e];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c.quat[i] = S.cube[(3 + i) * n + e];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c.v[i] = S.cube[(7 + i) * n + e];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c.w[i] = S.cube[(10 + i) * n + e];
+}
+
+__device__ __forceinline__ void store_cube(const StatePtrs& S, int n, int e, const cube::State& c) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.cube[(0 + i) * n + e] = c.pos[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) S.cube[(3 + i) * n + e] = c.quat[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.cube[(7 + i) * n + e] = c.v[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.cube[(10 + i) * n + e] = c.w[i];
+}
+
+template <int TASK>
+__device__ __forceinline__ void make_obs(const float (&ee)[3], const float (&goal)[3], const cube::State& cb,
+                                         float (&o)[TaskTraits<TASK>::OBS]) {
+  o[0] = ee[0]; o[1] = ee[1]; o[2] = ee[2];
+  if constexpr (TASK == ARMSIM_TASK_REACH) {
+    o[3] = goal[0]; o[4] = goal[1]; o[5] = goal[2];
+  } else if constexpr (TaskTraits<TASK>::HAS_CUBE) {
+    o[3] = cb.pos[0]; o[4] = cb.pos[1]; o[5] = cb.pos[2];
+    o[6] = goal[0]; o[7] = goal[1]; o[8] = goal[2];
+  }
+}
+
+// Env.reset() for one env (rl_reach_env.py:132-217, rl_push_env.py:145-256, rl_pick_env.py:141-256).  Draws come from
+// Philox4x32-10 keyed by (seed, global env id, episode); formulas follow the reference: random.uniform(a,b) = a+(b-a)u.
+template <int TASK>
+__device__ __forceinline__ void reset_env(const ChainParams& C, const TaskParams& T, const StatePtrs& S, int e,
+                                          float (&o)[TaskTraits<TASK>::OBS]) {
+  const int n = T.n;
+  const unsigned long long gid = T.gid_offset + (unsigned long long)e;
+  const uint32_t ep = (uint32_t)S.episode[e];
+  float q[NJ], goal[3], u[4];
+  cube::State cb;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) { q[j] = T.init_q[j]; S.q[j * n + e] = q[j]; }
+  if constexpr (!TaskTraits<TASK>::HAS_CUBE) {
+    reset_uniforms(T, gid, ep, 0u, u);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) goal[i] = __fmaf_rn(T.goal_span[i], u[i], T.goal_lo[i]);
+  } else {
+    float cx = 0.f, cy = 0.f, cz = 0.f, cyaw = 0.f;
+    for (uint32_t attempt = 0; attempt < 1000u; ++attempt) {   // rejection loop rl_push_env.py:195-214
+      float v[4];
+      reset_uniforms(T, gid, ep, 2u * attempt, u);
+      reset_uniforms(T, gid, ep, 2u * attempt + 1u, v);
+      cx = __fmaf_rn(T.goal_span[0], u[0], T.goal_lo[0]);
+      cy = __fmaf_rn(T.goal_span[1], u[1], T.goal_lo[1]);
+      cz = 0.01f;
+      cyaw = __fmaf_rn(3.1415925438f, u[2], 1.57f);
+      goal[0] = __fmaf_rn(T.goal_span[0], u[3], T.goal_lo[0]);
+      goal[1] = __fmaf_rn(T.goal_span[1], v[0], T.goal_lo[1]);
+      goal[2] = (TASK == ARMSIM_TASK_PICK) ? __fmaf_rn(T.goal_span[2], v[1], T.goal_lo[2]) : 0.01f;
+      const float dx = __fsub_rn(cx, goal[0]), dy = __fsub_rn(cy, goal[1]), dz = __fsub_rn(cz, goal[2]);
+      const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+      const float d = __fsqrt_rn(d2);
+      if (d >= 0.22f && d <= 0.25f) break;
+    }
+    cube::init(cb, cx, cy, cz, cyaw);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.goal[i * n + e] = goal[i];
+  S.step[e] = 0;
+  S.done[e] = 0;
+  S.ik_iters[e] = 0;
+  S.episode[e] = (int)(ep + 1u);
+  float p[3], R[9], P[NJ][3], Z[NJ][3];
+  chain_fk<false>(C, q, p, R, P, Z);
+  if constexpr (TaskTraits<TASK>::HAS_CUBE) {
+    S.grip[e] = 0.f;
+    cube::step(cb, p, R, TASK == ARMSIM_TASK_PICK, 0.f);   // p.stepSimulation() rl_push_env.py:242
+    const float d0 = cb.pos[0] - goal[0], d1 = cb.pos[1] - goal[1], d2 = cb.pos[2] - goal[2];
+    S.last_dist[e] = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    store_cube(S, n, e, cb);
+  }
+  make_obs<TASK>(p, goal, cb, o);
+}
+
+// Env.step() for one env.  Returns through o / r / d / su.
+template <int TASK>
+__device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams& T, const StatePtrs& S, int e,
+                                         const float (&a)[3], float (&o)[TaskTraits<TASK>::OBS], float& r, uint8_t& d,
+                                         uint8_t& su) {
+  const int n = T.n;
+  float q[NJ], goal[3];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) q[j] = S.q[j * n + e];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) goal[i] = S.goal[i * n + e];
+  int stepc = S.step[e];
+  cube::State cb;
+  if constexpr (TaskTraits<TASK>::HAS_CUBE) load_cube(S, n, e, cb);
+
+  float p[3], R[9], P[NJ][3], Z[NJ][3];
+  if (!T.auto_reset && S.done[e]) {   // finished env waiting for reset: report its frozen state
+    chain_fk<false>(C, q, p, R, P, Z);
+    make_obs<TASK>(p, goal, cb, o);
+    r = 0.f; d = 1; su = 0;
+    return;
+  }
+  chain_fk<true>(C, q, p, R, P, Z);                               // current_pos = getLinkState(...)[4]  :237
+  float tgt[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    tgt[i] = fmaf(a[i], T.dv, p[i]);                              // :232-234, :239-242
+    if constexpr (TASK != ARMSIM_TASK_KUKA_REACH) tgt[i] = clampf(tgt[i], T.ws_lo[i], T.ws_hi[i]);
+  }
+  const float q6_old = q[NJ - 1];
+  const int its = ik_solve(C, T, tgt, q, p, R, P, Z);             // :244-250
+  bool refk = false;
+  if (T.napply < NJ) { q[NJ - 1] = q6_old; refk = true; }         // rl_pick_env.py:342 only joints 0..5 are teleported
+  if (T.clamp) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) q[j] = clampf(q[j], C.lower[j], C.upper[j]);
+    refk = true;
+  }
+  if (refk) chain_fk<false>(C, q, p, R, P, Z);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) S.q[j * n + e] = q[j];             // resetJointState :252-257
+  S.ik_iters[e] = its;
+  stepc += 1;                                                     // :264
+
+  bool term = false, succ = false;
+  if constexpr (TASK == ARMSIM_TASK_REACH) {
+    const float d0 = p[0] - goal[0], d1 = p[1] - goal[1], d2 = p[2] - goal[2];
+    const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);       // :281
+    if (stepc > T.max_steps) { r = -dist * 10.f; term = true; }  // :299-301
+    else if (dist < T.reach_dis) { r = 0.f; term = true; succ = true; }  // :303-306
+    else { r = -dist * 10.f; }                                    // :307-309
+  } else if constexpr (TASK == ARMSIM_TASK_KUKA_REACH) {
+    const float d0 = p[0] - goal[0], d1 = p[1] - goal[1], d2 = p[2] - goal[2];
+    const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    const bool oob = p[0] < T.ws_lo[0] || p[0] > T.ws_hi[0] || p[1] < T.ws_lo[1] || p[1] > T.ws_hi[1] ||
+                     p[2] < T.ws_lo[2] || p[2] > T.ws_hi[2];     // kuka_reach_env.py:276-278
+    if (oob) { r = -1.f; term = true; }
+    else if (stepc > T.max_steps) { r = -1.f; term = true; }
+    else if (dist < T.reach_dis) { r = 10.f; term = true; succ = true; }
+    else { r = 0.f; }
+  } else {
+    constexpr bool PICK = TASK == ARMSIM_TASK_PICK;
+    float grip = S.grip[e];
+    cube::step(cb, p, R, PICK, grip);                             // p.stepSimulation() rl_push_env.py:349
+    if constexpr (PICK) {
+      if (grip < 0.5f && cube::gripper_distance(cb, p, R) < cube::CLOSE_DIST) {   // rl_pick_env.py:412-416
+        const float h0 = cb.pos[0] - (p[0] + cube::GRIPPER_LEN * R[2]);
+        const float h1 = cb.pos[1] - (p[1] + cube::GRIPPER_LEN * R[5]);
+        const float h2 = cb.pos[2] - (p[2] + cube::GRIPPER_LEN * R[8]);
+        grip = sqrtf(h0 * h0 + h1 * h1 + h2 * h2) < cube::HOLD_DIST ? 2.f : 1.f;
+      }
+      cube::step(cb, p, R, PICK, grip);                           // second p.stepSimulation() :417
+      S.grip[e] = grip;
+    }
+    const float d0 = cb.pos[0] - goal[0], d1 = cb.pos[1] - goal[1], d2 = cb.pos[2] - goal[2];
+    const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);       // rl_push_env.py:383 / :393
+    float test = dist - S.last_dist[e];                           // :385
+    if (fabsf(test) < 1e-5f) test = 0.01f;                        // :386-387
+    S.last_dist[e] = dist;
+    if (stepc > T.max_steps) { r = -dist * 50.f; term = true; }   // :417-419
+    else if (dist < 0.05f) { r = 100.f; term = true; }            // :421-423
+    else { r = -test * 100.f; }                                   // :424-428
+    succ = dist < T.reach_dis;                                    // _is_success :442-445
+    store_cube(S, n, e, cb);
+  }
+  S.step[e] = stepc;
+  d = term ? 1 : 0;
+  su = succ ? 1 : 0;
+  if (term && T.auto_reset) {
+    reset_env<TASK>(C, T, S, e, o);
+  } else {
+    if (term) S.done[e] = 1;
+    make_obs<TASK>(p, goal, cb, o);
+  }
+}
+
+template <int TASK>
+__global__ void __launch_bounds__(LANE_BLOCK)
+step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T, const StatePtrs S,
+                 const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
+                 uint8_t* __restrict__ done, uint8_t* __restrict__ success) {
+  constexpr int OD = TaskTraits<TASK>::OBS;
+  __shared__ float s_act[LANE_BLOCK * 3];
+  __shared__ float s_obs[LANE_BLOCK * OD];
+  const int base = blockIdx.x * LANE_BLOCK;
+  const int cnt = min(LANE_BLOCK, T.n - base);
+  for (int i = threadIdx.x; i < cnt * 3; i += LANE_BLOCK) s_act[i] = action[(size_t)base * 3 + i];
+  __syncthreads();
+  const int e = base + threadIdx.x;
+  if (threadIdx.x < cnt) {
+    const float a[3] = {s_act[threadIdx.x * 3], s_act[threadIdx.x * 3 + 1], s_act[threadIdx.x * 3 + 2]};
+    float o[OD], r;
+    uint8_t d, su;
+    step_env<TASK>(C, T, S, e, a, o, r, d, su);
+#pragma unroll
+    for (int k = 0; k < OD; ++k) s_obs[threadIdx.x * OD + k] = o[k];
+    reward[e] = r;
+    done[e] = d;
+    success[e] = su;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cnt * OD; i += LANE_BLOCK) obs[(size_t)base * OD + i] = s_obs[i];
+}
+
+template <int TASK>
+__global__ void __launch_bounds__(LANE_BLOCK)
+reset_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T, const StatePtrs S,
+                  const uint8_t* __restrict__ mask, float* __restrict__ obs) {
+  constexpr int OD = TaskTraits<TASK>::OBS;
+  const int e = blockIdx.x * LANE_BLOCK + threadIdx.x;
+  if (e >= T.n) return;
+  if (mask && !mask[e]) return;
+  float o[OD];
+  reset_env<TASK>(C, T, S, e, o);
+  if (obs) {
+#pragma unroll
+    for (int k = 0; k < OD; ++k) obs[(size_t)e * OD + k] = o[k];
+  }
+}
+
+// FK of a host-supplied batch (armsim_fk_host): q [n,7] row-major -> pos [n,3], rot [n,9]
+__global__ void fk_kernel(const __grid_constant__ ChainParams C, int n, const float* __restrict__ qin, float* __restrict__ pos,
+                          float* __restrict__ rot) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float q[NJ], p[3], R[9], P[NJ][3], Z[NJ][3];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) q[j] = qin[(size_t)e * NJ + j];
+  chain_fk<false>(C, q, p, R, P, Z);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) pos[(size_t)e * 3 + i] = p[i];
+  if (rot) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rot[(size_t)e * 9 + i] = R[i];
+  }
+}

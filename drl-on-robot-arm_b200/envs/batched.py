@@ -1,0 +1,138 @@
+"""BatchedArmEnv -- N_envs reference environments stepped by ONE fused CUDA launch.
+
+Host-side mirror of the reference Env API for a whole batch: reset() -> obs [N, obs_dim], step(action [N, 3]) ->
+(obs, reward [N], done [N], success [N]).  Tensors live on the GPU; the call goes straight through the C-ABI
+(armsim_step) with raw device pointers on torch's current stream -- PyTorch is only the allocator / stream owner.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib as L
+
+_TASKS = {"reach": L.TASK_REACH, "push": L.TASK_PUSH, "pick": L.TASK_PICK, "kuka_reach": L.TASK_KUKA_REACH}
+_ROBOTS = {"kuka_iiwa": L.ROBOT_KUKA_IIWA, "diana_s1": L.ROBOT_DIANA_S1}
+
+
+class ArmSimHandle:
+    """Thin RAII wrapper of an ArmSim* (create / destroy / state io); no torch needed."""
+
+    def __init__(self, task="reach", n_envs=1, device=0, robot="kuka_iiwa", seed=0, env_id_offset=0, auto_reset=False,
+                 chain=None, **overrides):
+        task_id = _TASKS[task] if isinstance(task, str) else int(task)
+        cfg = L.default_config(task_id, **overrides)
+        cfg.n_envs = int(n_envs)
+        cfg.device = int(device)
+        cfg.seed = int(seed)
+        cfg.env_id_offset = int(env_id_offset)
+        cfg.auto_reset = 1 if auto_reset else 0
+        self._chain = None
+        if chain is not None:
+            self._chain = chain          # keep alive: cfg holds a raw pointer
+            cfg.robot = L.ROBOT_CUSTOM
+            cfg.custom_chain = C.pointer(chain)
+        else:
+            cfg.robot = _ROBOTS[robot] if isinstance(robot, str) else int(robot)
+        self.cfg = cfg
+        h = C.c_void_p()
+        L.check(L.lib().armsim_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.n = int(n_envs)
+        self.obs_dim = L.lib().armsim_obs_dim(h)
+        self.act_dim = L.lib().armsim_action_dim(h)
+        self.task = task_id
+
+    def close(self):
+        if getattr(self, "h", None):
+            L.lib().armsim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state injection / read-back (parity tests, checkpointing)
+    def set_state(self, field, arr):
+        a = np.ascontiguousarray(arr, np.int32 if field in L.INT_FIELDS else np.float32)
+        L.check(L.lib().armsim_set_state(self.h, field, a.ctypes.data, a.nbytes))
+
+    def get_state(self, field):
+        w = L.FIELD_WIDTH[field]
+        a = np.zeros((self.n, w) if w > 1 else (self.n,), np.int32 if field in L.INT_FIELDS else np.float32)
+        L.check(L.lib().armsim_get_state(self.h, field, a.ctypes.data, a.nbytes))
+        return a
+
+    def fk(self, q):
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, 7)
+        pos = np.zeros((q.shape[0], 3), np.float32)
+        rot = np.zeros((q.shape[0], 9), np.float32)
+        L.check(L.lib().armsim_fk_host(self.h, q.ctypes.data, q.shape[0], pos.ctypes.data, rot.ctypes.data))
+        return pos, rot.reshape(-1, 3, 3)
+
+    @property
+    def launch_count(self):
+        return int(L.lib().armsim_launch_count(self.h))
+
+    # ---- host-buffer path (numpy in / numpy out; H2D + launch + D2H inside the call)
+    def step_host(self, action, out=None):
+        a = np.ascontiguousarray(action, np.float32)
+        if a.shape != (self.n, self.act_dim):
+            raise ValueError("action must be [%d, %d], got %s" % (self.n, self.act_dim, a.shape))
+        if out is None:
+            out = (np.empty((self.n, self.obs_dim), np.float32), np.empty(self.n, np.float32),
+                   np.empty(self.n, np.uint8), np.empty(self.n, np.uint8))
+        obs, rew, done, succ = out
+        L.check(L.lib().armsim_step_host(self.h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
+                                         succ.ctypes.data))
+        return obs, rew, done, succ
+
+    def reset_host(self, mask=None, obs=None):
+        if obs is None:
+            obs = np.zeros((self.n, self.obs_dim), np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        L.check(L.lib().armsim_reset_host(self.h, None if m is None else m.ctypes.data, obs.ctypes.data))
+        return obs
+
+
+class BatchedArmEnv(ArmSimHandle):
+    """Vectorised env on one GPU: torch CUDA tensors in, torch CUDA tensors out, zero host round trips."""
+
+    def __init__(self, task="reach", n_envs=4096, device=None, **kw):
+        import torch
+        if not torch.cuda.is_available():
+            raise L.ArmsimError("BatchedArmEnv needs a CUDA device (no CPU fallback)")
+        self.torch = torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        super().__init__(task=task, n_envs=n_envs, device=idx, **kw)
+        self.device = torch.device("cuda", idx)
+        n, od = self.n, self.obs_dim
+        self.obs = torch.empty((n, od), dtype=torch.float32, device=self.device)
+        self.reward = torch.empty((n,), dtype=torch.float32, device=self.device)
+        self.done = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        self.success = torch.empty((n,), dtype=torch.uint8, device=self.device)
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset(self, mask=None):
+        m = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
+            m = mask.data_ptr()
+        L.check(L.lib().armsim_reset(self.h, m, self.obs.data_ptr(), self._stream()))
+        return self.obs
+
+    def step(self, action, out=None):
+        """action: float32 CUDA tensor [N, 3].  Returns (obs, reward, done, success) views of the env's own output
+        buffers (overwritten by the next step) unless `out` = (obs, reward, done, success) tensors is given."""
+        t = self.torch
+        if action.dtype != t.float32 or not action.is_cuda or not action.is_contiguous() or \
+                tuple(action.shape) != (self.n, self.act_dim):
+            action = action.to(device=self.device, dtype=t.float32).reshape(self.n, self.act_dim).contiguous()
+        obs, rew, done, succ = out if out is not None else (self.obs, self.reward, self.done, self.success)
+        L.check(L.lib().armsim_step(self.h, action.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                    succ.data_ptr(), self._stream()))
+        return obs, rew, done, succ

@@ -1,0 +1,163 @@
+/* armsim.h -- C-ABI of the B200-native batched robot-arm step engine (libarmsim.so).
+ *
+ * Drop-in boundary for ONE hot path of Shimly-2/DRL-on-robot-arm: the gym-style Env.reset()/Env.step()
+ * of envs/rl_reach_env.py, envs/rl_push_env.py, envs/rl_pick_env.py and envs/kuka_reach_env.py, which in the
+ * reference drive ONE arm per process through pybullet on the CPU.  The reference has no FFI of its own (its
+ * boundary is Python duck-typing of gym.Env, main.py:83 `getattr(envs, opt.env)(...)`, envs/__init__.py:1-3);
+ * these entry points are what a ctypes/pybind binding inside those Env classes binds to.
+ *
+ * Conventions
+ *   - plain C types, pointers and sizes only; no exceptions cross the ABI; 0 = OK, negative = ARMSIM_E_*;
+ *     armsim_last_error() returns a thread-local message for the last failing call.
+ *   - `*_dev` pointers are CUDA device pointers on the handle's device, `*_host` pointers are host memory;
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry points are
+ *     asynchronous on `stream` and never synchronise; the *_host entry points synchronise before returning.
+ *   - the caller owns every I/O buffer; the library owns the per-env state (struct-of-arrays in HBM).
+ *   - one handle per GPU; a handle is not thread-safe.
+ *   - there is NO CPU fallback: armsim_create fails with ARMSIM_E_CUDA when no CUDA device is usable.
+ */
+#ifndef ARMSIM_H
+#define ARMSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARMSIM_ABI_VERSION 1
+#define ARMSIM_NJ 7            /* arm joints (Kuka iiwa, DianaS1) */
+#define ARMSIM_ACT_DIM 3       /* Cartesian EE servo action, reference envs' action_space */
+#define ARMSIM_TORQUE_DIM 7    /* torque mode action */
+
+/* error codes */
+#define ARMSIM_OK 0
+#define ARMSIM_E_INVALID (-1)  /* bad argument / config */
+#define ARMSIM_E_CUDA (-2)     /* CUDA runtime error (message has the cudaError string) */
+#define ARMSIM_E_NOMEM (-3)
+#define ARMSIM_E_STATE (-4)    /* unknown state field / wrong size */
+
+/* tasks: which reference Env.step the fused kernel reproduces */
+enum {
+  ARMSIM_TASK_REACH = 0,       /* envs/rl_reach_env.py:219-319   obs f32[6] = [ee, goal]            */
+  ARMSIM_TASK_PUSH = 1,        /* envs/rl_push_env.py:310-445    obs f32[9] = [ee, cube, target]    */
+  ARMSIM_TASK_PICK = 2,        /* envs/rl_pick_env.py:310-450    obs f32[9] = [link-6, cube, target]*/
+  ARMSIM_TASK_KUKA_REACH = 3   /* envs/kuka_reach_env.py:214-305 obs f32[3] = ee                    */
+};
+enum { ARMSIM_ROBOT_KUKA_IIWA = 0, ARMSIM_ROBOT_DIANA_S1 = 1, ARMSIM_ROBOT_CUSTOM = 2 };
+enum {
+  ARMSIM_MODE_IK_TELEPORT = 0, /* what the reference does: EE target -> DLS IK -> teleport joints */
+  ARMSIM_MODE_TORQUE = 1       /* north-star addition: joint torques -> ABA forward dynamics -> integrate      */
+};
+enum {
+  ARMSIM_MAP_AUTO = 0,         /* pick by n_envs */
+  ARMSIM_MAP_LANE = 1,         /* one CUDA lane per arm (throughput mapping, SoA state)        */
+  ARMSIM_MAP_WARP = 2          /* one warp per arm, joints across lanes (latency mapping)      */
+};
+
+/* A custom 7-DoF serial chain (ARMSIM_ROBOT_CUSTOM).  Same content as include/armsim_robot_models.h. */
+typedef struct ArmsimChain {
+  double base_xyz[3], base_rpy[3];
+  double xyz[ARMSIM_NJ][3], rpy[ARMSIM_NJ][3];         /* joint origin in parent link frame; joint axis = local +z */
+  double lower[ARMSIM_NJ], upper[ARMSIM_NJ], effort[ARMSIM_NJ], velocity[ARMSIM_NJ], damping[ARMSIM_NJ];
+  double mass[ARMSIM_NJ], com[ARMSIM_NJ][3], inertia[ARMSIM_NJ][6];
+} ArmsimChain;
+
+typedef struct ArmsimConfig {
+  int32_t struct_size;         /* = sizeof(ArmsimConfig), ABI guard */
+  int32_t task, robot, mode, mapping;
+  int32_t n_envs;              /* envs owned by THIS handle (this rank's shard) */
+  int32_t device;              /* CUDA ordinal */
+  int32_t auto_reset;          /* 1: envs that finish are re-initialised inside the same launch (obs = first obs of
+                                  the next episode; reward/done/success describe the finished step) */
+  uint64_t seed;               /* Philox key */
+  uint64_t env_id_offset;      /* global id of env 0 (sharding: results do not depend on the rank layout) */
+  double dv;                   /* EE metres per unit action: opt.reach_ctr 0.02 (config.py:41) / 0.08 push,pick / 0.005 kuka_reach */
+  double reach_dis;            /* success distance: opt.reach_dis 0.01 (config.py:42); 0.05 push/pick; 0.1 kuka_reach */
+  int32_t max_steps;           /* opt.max_steps_one_episode 500 (config.py:51): done when step_counter > max_steps */
+  double ws_lo[3], ws_hi[3];   /* EE target clip box (rl_reach_env.py:221-223); kuka_reach: OOB box, no clip */
+  double goal_lo[3], goal_hi[3];/* reset sampling box for goal / cube / target (rl_reach_env.py:180-182) */
+  double target_rpy[3];        /* IK target orientation euler(0,-pi,pi/2) (rl_reach_env.py:121-122) */
+  double init_q[ARMSIM_NJ];    /* init_joint_positions (rl_reach_env.py:116-119) */
+  double ik_damping;           /* jointDamping 1e-5 (rl_reach_env.py:111-113) */
+  int32_t ik_max_iters;        /* Bullet default 20 */
+  double ik_residual;          /* Bullet default 1e-4 */
+  int32_t clamp_joint_limits;  /* 0 = reference behaviour (no clamp in IK mode); torque mode always clamps */
+  int32_t reserved[7];
+  const ArmsimChain* custom_chain; /* only for ARMSIM_ROBOT_CUSTOM */
+} ArmsimConfig;
+
+typedef struct ArmSim ArmSim;  /* opaque handle */
+
+/* state fields for armsim_get_state / armsim_set_state (host arrays, row-major [n_envs, width]) */
+enum {
+  ARMSIM_F_Q = 0,              /* f32 [n,7]  joint angles                         */
+  ARMSIM_F_QD = 1,             /* f32 [n,7]  joint velocities (torque mode)        */
+  ARMSIM_F_GOAL = 2,           /* f32 [n,3]  reach goal / push,pick target         */
+  ARMSIM_F_STEP = 3,           /* i32 [n]    step_counter                          */
+  ARMSIM_F_EPISODE = 4,        /* i32 [n]    episodes started (Philox counter)     */
+  ARMSIM_F_CUBE_POS = 5,       /* f32 [n,3]                                        */
+  ARMSIM_F_CUBE_QUAT = 6,      /* f32 [n,4]  xyzw                                  */
+  ARMSIM_F_CUBE_LINVEL = 7,    /* f32 [n,3]                                        */
+  ARMSIM_F_CUBE_ANGVEL = 8,    /* f32 [n,3]                                        */
+  ARMSIM_F_LAST_DIST = 9,      /* f32 [n]    previous cube-target distance (push reward) */
+  ARMSIM_F_GRIP = 10,          /* f32 [n]    pick: 1 = fingers closed              */
+  ARMSIM_F_IK_ITERS = 11,      /* i32 [n]    read-only: DLS iterations used by the last step */
+  ARMSIM_F_COUNT = 12
+};
+
+/* Fill *cfg with the reference constants for `task` (robot kuka_iiwa, IK-teleport mode, n_envs = 1). */
+int armsim_default_config(int32_t task, ArmsimConfig* cfg);
+
+/* Create n_envs simulators on cfg->device and reset them all (episode 0).  Replaces Env.__init__
+ * (rl_reach_env.py:44-125: p.connect + constants + first reset). */
+int armsim_create(const ArmsimConfig* cfg, ArmSim** out);
+
+/* Env.close() (rl_reach_env.py:321-322). */
+void armsim_destroy(ArmSim* sim);
+
+/* Env.reset() for the envs whose mask byte is non-zero (mask_dev == NULL: all).  Replaces rl_reach_env.py:132-217 /
+ * rl_push_env.py:145-256 / rl_pick_env.py:141-256.  obs_dev f32 [n, obs_dim] may be NULL. */
+int armsim_reset(ArmSim* sim, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* Env.step(action) for the whole batch in ONE kernel launch.  Replaces rl_reach_env.py:219-319 (and the push /
+ * pick / kuka_reach equivalents): EE servo + IK + teleport + cube/gripper contact + reward + done, fused.
+ *   action_dev  f32 [n, 3]  (IK mode)  or f32 [n, 7] joint torques (torque mode)
+ *   obs_dev     f32 [n, obs_dim]
+ *   reward_dev  f32 [n]
+ *   done_dev    u8  [n]
+ *   success_dev u8  [n]     reach: is_success; push/pick: info['is_success']; kuka_reach: distance < 0.1
+ * Envs already done (auto_reset = 0) are left untouched and report reward 0, done 1. */
+int armsim_step(ArmSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                uint8_t* success_dev, void* stream);
+
+/* Same step through HOST buffers (what a host-side Env.step sees): pinned staging, H2D of the actions, the
+ * fused launch, D2H of obs/reward/done/success, stream synchronise.  Used for the end-to-end measurement. */
+int armsim_step_host(ArmSim* sim, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                     uint8_t* success_host);
+int armsim_reset_host(ArmSim* sim, const uint8_t* mask_host, float* obs_host);
+
+/* Inject / read back per-env state (parity tests inject q, goal, cube pose; SURVEY 5 "seeding facts").
+ * `bytes` must equal n_envs * width * 4.  Synchronous. */
+int armsim_set_state(ArmSim* sim, int32_t field, const void* host_src, size_t bytes);
+int armsim_get_state(ArmSim* sim, int32_t field, void* host_dst, size_t bytes);
+
+/* Introspection */
+int32_t armsim_obs_dim(const ArmSim* sim);
+int32_t armsim_action_dim(const ArmSim* sim);
+int32_t armsim_n_envs(const ArmSim* sim);
+int32_t armsim_mapping(const ArmSim* sim);        /* resolved ARMSIM_MAP_* */
+int64_t armsim_launch_count(const ArmSim* sim);   /* kernels launched by this handle so far */
+int32_t armsim_abi_version(void);
+const char* armsim_last_error(void);
+
+/* Forward kinematics of the handle's chain for a host batch q[n,7] -> pos[n,3], rot[n,9] (row-major), computed
+ * on the device by the same routine the step kernel uses.  Synchronous; for tests and for Env shims that need
+ * getLinkState-style queries. */
+int armsim_fk_host(ArmSim* sim, const float* q_host, int32_t n, float* pos_host, float* rot_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARMSIM_H */

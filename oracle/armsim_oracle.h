@@ -1,0 +1,57 @@
+/* armsim_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, fp64) of the reference hot path, used ONLY as the checker by tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  Nothing under
+ * drl-on-robot-arm_b200/ may link, import or call this library.
+ *
+ * Parity status: FK / workspace clip / reward / done / success / episode length are PINNED by the
+ * reference's own artefacts (main.py:106 golden EE vector, envs/bmirobot_joints_info_pybullet.txt fixture, the
+ * Python control flow).  The arithmetic that lives in the third-party dependency pybullet==3.0.6 (ReadMe.md:17;
+ * source absent from /root/reference, wheel not installable) -- calculateInverseKinematics and stepSimulation --
+ * is restated from Bullet's published algorithm and is PARITY UNPINNED: no reference test or fixture fixes its
+ * numerics.
+ */
+#ifndef ARMSIM_ORACLE_H
+#define ARMSIM_ORACLE_H
+#include <stdint.h>
+#include "armsim.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OrcSim OrcSim;
+
+/* Philox4x32-10 (Salmon et al. 2011), the counter-based generator the device reset uses. */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* the 4 uniforms in [0,1) of reset draw `block` of (seed, global env id, episode) */
+void orc_reset_uniforms(uint64_t seed, uint64_t env_gid, uint32_t episode, uint32_t block, float u[4]);
+
+/* forward kinematics of a built-in chain (robot = ARMSIM_ROBOT_*): EE (link-7 frame) position, rotation (row-major),
+ * the 7 joint-frame origins and world joint axes.  Any output may be NULL. */
+int orc_fk(int32_t robot, const double q[7], double pos[3], double rot[9], double origins[21], double axes[21]);
+/* 6x7 geometric Jacobian of the EE link frame, rows 0-2 linear, 3-5 angular, row-major */
+int orc_jacobian(int32_t robot, const double q[7], double J[42]);
+/* Bullet calculateInverseKinematics restated.  Returns the iteration count. */
+int orc_ik(int32_t robot, const double q_in[7], const double target_pos[3], const double target_quat_xyzw[4],
+           double damping, int max_iters, double residual, double q_out[7], double* final_diff);
+void orc_quat_from_euler(const double rpy[3], double quat_xyzw[4]);
+
+OrcSim* orc_create(const ArmsimConfig* cfg);
+void orc_destroy(OrcSim* s);
+void orc_reset(OrcSim* s, const uint8_t* mask, float* obs);
+/* one Env.step for envs [lo, hi) (disjoint ranges may run on different threads) */
+void orc_step_range(OrcSim* s, int32_t lo, int32_t hi, const float* action, float* obs, double* reward, uint8_t* done,
+                    uint8_t* success);
+void orc_step(OrcSim* s, const float* action, float* obs, double* reward, uint8_t* done, uint8_t* success);
+/* state access with the ARMSIM_F_* field ids; f32/i32 host arrays like armsim_set_state, plus an fp64 read-back */
+int orc_set_state(OrcSim* s, int32_t field, const void* src, size_t bytes);
+int orc_get_state(OrcSim* s, int32_t field, void* dst, size_t bytes);
+int orc_get_state_f64(OrcSim* s, int32_t field, double* dst, size_t count);
+int32_t orc_obs_dim(const OrcSim* s);
+int orc_default_config(int32_t task, ArmsimConfig* cfg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

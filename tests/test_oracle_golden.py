@@ -1,0 +1,285 @@
+"""CPU tests: the oracle against every golden vector / fixture the reference holds for the path, plus
+truth tables of the reward / done logic restated from envs/*.py.  No GPU, no /root/reference access."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PKG = os.path.join(os.path.dirname(GOLD), "..", "drl-on-robot-arm_b200")
+Q0 = [0.006418, 0.413184, -0.011401, -1.589317, 0.005379, 1.137684, -0.006539]
+
+
+# ------------------------------------------------------------------ Philox known answers (Random123 kat_vectors)
+@pytest.mark.parametrize("ctr,key,exp", [
+    ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+    ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+    ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+     [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+])
+def test_philox_known_answers(oracle, ctr, key, exp):
+    assert oracle.philox(ctr, key) == exp
+
+
+def test_reset_uniforms_range(oracle):
+    u = np.stack([oracle.reset_uniforms(3, g, e, b) for g in range(20) for e in range(3) for b in range(3)])
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0
+    assert 0.4 < u.mean() < 0.6
+
+
+# ------------------------------------------------------------------ golden vector main.py:106
+def test_fk_matches_main_py_106(oracle):
+    g = json.load(open(os.path.join(GOLD, "ee_init_main_py.json")))
+    pos, rot, _, _ = oracle.fk(g["init_joint_positions"])
+    # the reference value is float32-rounded: agree to one f32 ulp at 0.5 (6e-8)
+    assert np.abs(pos - np.array(g["ee"])).max() <= 6.0e-8
+    assert np.array_equal(np.float32(pos)[1:], np.float32(g["ee"])[1:])
+    assert np.allclose(rot @ rot.T, np.eye(3), atol=1e-12) and abs(np.linalg.det(rot) - 1) < 1e-12
+    assert np.allclose(rot, np.diag([-1, 1, -1]), atol=2e-3)       # R ~ diag(-1, 1, -1)
+
+
+# ------------------------------------------------------------------ getJointInfo fixture (bmirobot_joints_info_pybullet.txt)
+def _rpy(r, p, y):
+    cr, sr, cp, sp, cy, sy = math.cos(r), math.sin(r), math.cos(p), math.sin(p), math.cos(y), math.sin(y)
+    return np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                     [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                     [-sp, cp * sr, cp * cr]])
+
+
+def _quat_to_mat(q):
+    x, y, z, w = np.array(q) / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+@pytest.mark.parametrize("robot,first", [("kuka_iiwa", 0), ("diana_s1", 1)])
+def test_chain_matches_joint_info_fixture(robot, first):
+    fix = json.load(open(os.path.join(GOLD, "joint_info_fixture.json")))[robot]
+    model = json.load(open(os.path.join(PKG, "robots", robot + ".json")))
+    parent_com = np.array(model["base_inertial_xyz"])
+    for k, j in enumerate(model["joints"]):
+        t = fix[first + k]
+        assert t[1] == j["name"] and t[2] == 0                      # revolute
+        assert t[8] == pytest.approx(j["lower"], abs=1e-9) and t[9] == pytest.approx(j["upper"], abs=1e-9)
+        assert t[6] == j["damping"] and t[10] == j["effort"] and t[11] == pytest.approx(j["velocity"])
+        assert t[13] == [0.0, 0.0, 1.0]                              # all joints about local +z
+        assert np.allclose(np.array(j["xyz"]) - parent_com, t[14], atol=1e-9)   # parentFramePos
+        assert np.allclose(_quat_to_mat(t[15]), _rpy(*j["rpy"]).T, atol=1e-9)   # parentFrameOrn = inverse(rpy)
+        assert t[16] == first + k - 1
+        parent_com = np.array(j["com"])
+
+
+@pytest.mark.parametrize("robot", [0, 1])
+def test_fk_independent_numpy_chain(oracle, robot):
+    """oracle FK == an independent numpy product of homogeneous transforms built from robots/*.json"""
+    model = json.load(open(os.path.join(PKG, "robots", ("kuka_iiwa", "diana_s1")[robot] + ".json")))
+    rng = np.random.default_rng(robot)
+    for _ in range(20):
+        q = rng.uniform(-2, 2, 7)
+        R, p = _rpy(*model["base_rpy"]), np.array(model["base_xyz"], float)
+        for j, qi in zip(model["joints"], q):
+            p = p + R @ np.array(j["xyz"])
+            R = R @ _rpy(*j["rpy"]) @ _rpy(0, 0, qi)
+        pos, rot, _, _ = oracle.fk(q, robot)
+        assert np.allclose(pos, p, atol=1e-12) and np.allclose(rot, R, atol=1e-12)
+
+
+def test_jacobian_finite_difference(oracle):
+    rng = np.random.default_rng(5)
+    for _ in range(10):
+        q = rng.uniform(-1.5, 1.5, 7)
+        J = oracle.jacobian(q)
+        p0, R0, _, _ = oracle.fk(q)
+        for j in range(7):
+            dq = np.zeros(7)
+            dq[j] = 1e-6
+            p1, R1, _, _ = oracle.fk(q + dq)
+            assert np.allclose((p1 - p0) / 1e-6, J[:3, j], atol=1e-5)
+            W = (R1 @ R0.T - np.eye(3)) / 1e-6                       # skew(omega)
+            assert np.allclose([W[2, 1], W[0, 2], W[1, 0]], J[3:, j], atol=1e-5)
+
+
+# ------------------------------------------------------------------ IK contract (Bullet: residual 1e-4, <= 20 iterations)
+def test_ik_contract(oracle):
+    tq = oracle.quat_from_euler([0, -math.pi, math.pi / 2])
+    assert np.allclose(np.abs(tq), [math.sqrt(0.5), math.sqrt(0.5), 0, 0], atol=1e-12)
+    rng = np.random.default_rng(2)
+    p0, _, _, _ = oracle.fk(Q0)
+    q = np.array(Q0)
+    hist = np.zeros(21, int)
+    for k in range(200):
+        tgt = np.clip(oracle.fk(q)[0] + rng.uniform(-0.7, 0.7, 3) * 0.02, [0.2, -0.3, 0], [0.7, 0.3, 0.55])
+        qn, its, diff = oracle.ik(q, tgt, tq)
+        assert 1 <= its <= 20 and diff <= 1e-4
+        assert np.linalg.norm(oracle.fk(qn)[0] - tgt) <= 1e-4
+        hist[its] += 1
+        q = qn
+    assert hist[1:4].sum() >= 195           # 1-3 iterations typical for a 1.4 cm move
+    # orientation converges to the commanded one after the first steps (rl_reach_env.py:121-122)
+    R = oracle.fk(q)[1]
+    assert np.allclose(R, [[0, -1, 0], [-1, 0, 0], [0, 0, -1]], atol=2e-2)
+
+
+def test_ik_zero_iterations_keeps_q(oracle):
+    qn, its, diff = oracle.ik(Q0, [0.5, 0, 0.4], oracle.quat_from_euler([0, -math.pi, math.pi / 2]), max_iters=0)
+    assert its == 0 and np.array_equal(qn, Q0)
+
+
+# ------------------------------------------------------------------ reach step / reward truth table (rl_reach_env.py:267-319)
+def test_reach_reset_and_first_obs(oracle):
+    cfg = oracle.default_config(oracle.TASK_REACH, n_envs=64, seed=11)
+    s = oracle.OracleSim(cfg)
+    obs = s.reset()
+    g = json.load(open(os.path.join(GOLD, "ee_init_main_py.json")))
+    assert np.abs(obs[:, :3] - np.float32(g["ee"])).max() <= 6e-8           # every episode starts at main.py:106
+    goal = obs[:, 3:]
+    assert (goal >= [0.2, -0.3, 0.0]).all() and (goal <= [0.7, 0.3, 0.55]).all()   # :180-182
+    assert len(np.unique(goal[:, 0])) == 64
+    # the same (seed, env id, episode) always gives the same goal; a new episode gives a new one
+    s2 = oracle.OracleSim(oracle.default_config(oracle.TASK_REACH, n_envs=64, seed=11))
+    assert np.array_equal(s2.get_state(oracle.F_GOAL), s.get_state(oracle.F_GOAL)) is False  # s is one episode ahead
+    assert np.array_equal(s2.reset()[:, 3:], goal)
+
+
+def test_reach_truth_table(oracle):
+    O = oracle
+    s = O.OracleSim(O.default_config(O.TASK_REACH, n_envs=4))
+    ee0 = s.reset()[0, :3].astype(np.float64)
+    goals = np.tile(ee0, (4, 1))
+    goals[0] += [0.003, 0, 0]          # within reach_dis 0.01 after a zero action -> success
+    goals[1] += [0.2, 0, 0]            # far -> r = -10 d
+    goals[2] += [0.2, 0, 0]            # far + timeout
+    goals[3] += [0.003, 0, 0]          # close AND timeout: timeout branch wins (:299 before :303)
+    s.set_state(O.F_GOAL, goals.astype(np.float32))
+    s.set_state(O.F_STEP, np.array([0, 0, 500, 500], np.int32))
+    obs, r, d, su = s.step(np.zeros((4, 3), np.float32))
+    dist = np.linalg.norm(obs[:, :3].astype(np.float64) - obs[:, 3:].astype(np.float64), axis=1)
+    assert list(d) == [1, 0, 1, 1] and list(su) == [1, 0, 0, 0]
+    assert r[0] == 0.0
+    assert r[1] == pytest.approx(-10 * dist[1], abs=1e-6) and r[2] == pytest.approx(-10 * dist[2], abs=1e-6)
+    assert r[3] == pytest.approx(-10 * dist[3], abs=1e-6) and r[3] < 0
+    assert list(s.get_state(O.F_STEP)) == [1, 1, 501, 501]
+    # finished envs stay finished until reset (auto_reset = 0)
+    obs2, r2, d2, su2 = s.step(np.ones((4, 3), np.float32))
+    assert list(d2) == [1, 0, 1, 1] and r2[0] == 0 and np.array_equal(obs2[0], obs[0])
+    s.reset(mask=[1, 0, 0, 0])
+    assert list(s.get_state(O.F_STEP)) == [0, 2, 501, 501]
+
+
+def test_reach_episode_length_and_clip(oracle):
+    """an env that never reaches its goal terminates at step 501 (:299 `step_counter > 500`); EE target clipped (:239)"""
+    O = oracle
+    s = O.OracleSim(O.default_config(O.TASK_REACH, n_envs=2))
+    s.reset()
+    s.set_state(O.F_GOAL, np.array([[0.2, -0.3, 0.0]] * 2, np.float32))
+    a = np.array([[0.7, 0.7, 0.7], [-0.7, 0.7, 0.7]], np.float32)   # push into the +x+y+z / -x+y+z corners
+    n = 0
+    done = np.zeros(2)
+    while not done.all():
+        obs, r, done, su = s.step(a)
+        n += 1
+        assert n <= 501
+    assert n == 501 and not su.any()
+    assert np.allclose(obs[0, :3], [0.7, 0.3, 0.55], atol=1.5e-4)    # IK residual contract 1e-4
+    assert np.allclose(obs[1, :3], [0.2, 0.3, 0.55], atol=1.5e-4)
+
+
+def test_reach_auto_reset(oracle):
+    O = oracle
+    s = O.OracleSim(O.default_config(O.TASK_REACH, n_envs=3, auto_reset=1))
+    ee0 = s.reset()[0, :3].astype(np.float64)
+    g = np.tile(ee0 + [0.002, 0, 0], (3, 1)).astype(np.float32)
+    g[1] += 0.3
+    s.set_state(O.F_GOAL, g)
+    ep0 = s.get_state(O.F_EPISODE).copy()
+    obs, r, d, su = s.step(np.zeros((3, 3), np.float32))
+    assert list(d) == [1, 0, 1] and list(su) == [1, 0, 1]
+    ep1 = s.get_state(O.F_EPISODE)
+    assert list(ep1 - ep0) == [1, 0, 1]
+    assert list(s.get_state(O.F_STEP)) == [0, 1, 0]
+    assert not np.array_equal(obs[0, 3:], g[0])                       # obs already shows the next episode's goal
+    assert np.abs(obs[0, :3] - np.float32(ee0)).max() < 1e-6
+
+
+def test_kuka_reach_truth_table(oracle):
+    """kuka_reach_env.py:252-305: OOB -> -1 done; timeout (>1000) -> -1 done; d < 0.1 -> +10 done; else 0."""
+    O = oracle
+    s = O.OracleSim(O.default_config(O.TASK_KUKA_REACH, n_envs=4))
+    obs = s.reset()
+    assert obs.shape == (4, 3)
+    ee0 = obs[0].astype(np.float64)
+    goals = np.tile(ee0, (4, 1))
+    goals[0] += [0.05, 0, 0]
+    goals[1] += [0.3, 0, 0]
+    goals[2] += [0.3, 0, 0]
+    goals[3] += [0.05, 0, 0]
+    s.set_state(O.F_GOAL, goals.astype(np.float32))
+    s.set_state(O.F_STEP, np.array([0, 0, 1000, 0], np.int32))
+    q = s.get_state(O.F_Q)
+    a = np.zeros((4, 3), np.float32)
+    a[3] = [0, 0, 60.0]                 # dv 0.005 * 60 = 0.3 up: z 0.796 > 0.55 -> out of the box (no clip in this env)
+    obs, r, d, su = s.step(a)
+    assert list(r) == [10.0, 0.0, -1.0, -1.0] and list(d) == [1, 0, 1, 1] and list(su) == [1, 0, 0, 0]
+
+
+# ------------------------------------------------------------------ push: reset rule + untouched-cube known answer
+def test_push_reset_rejection_rule(oracle):
+    O = oracle
+    s = O.OracleSim(O.default_config(O.TASK_PUSH, n_envs=256, seed=3))
+    obs = s.reset()
+    cube0 = np.stack([obs[:, 3], obs[:, 4]], 1)
+    tgt = obs[:, 6:]
+    assert np.allclose(tgt[:, 2], 0.01)
+    d = np.linalg.norm(np.c_[cube0, np.full(256, 0.01)] - tgt, axis=1)
+    assert (d >= 0.22 - 1e-3).all() and (d <= 0.25 + 1e-3).all()            # rl_push_env.py:213 (cube has begun to fall)
+    assert (tgt[:, :2] >= [0.2, -0.3]).all() and (tgt[:, :2] <= [0.7, 0.3]).all()
+
+
+def test_push_untouched_cube_known_answer(oracle):
+    """an episode in which the cube is never touched returns ~500 x (-1) + (-50 d), d in [0.22, 0.25]
+    (the `|test| < 1e-5 -> 0.01` branch, rl_push_env.py:386-387,427, plus the timeout step :419), i.e. about
+    [-512.5, -511.0]; the reference's first logged returns are -512.2 .. -514.6 (visdata/push/origin_TD3).  The cube
+    is spawned 1.5 cm above the table (z 0.01 vs rest -0.005), and while it falls (~13 steps at 240 Hz) the change of
+    the cube-target distance exceeds 1e-5 for ~8 steps, which therefore score ~0 instead of -1: the model's
+    untouched return is ~-503.5.  Accept [-515, -500]."""
+    O = oracle
+    n = 16
+    s = O.OracleSim(O.default_config(O.TASK_PUSH, n_envs=n, seed=5))
+    s.reset()
+    ret = np.zeros(n)
+    a = np.zeros((n, 3), np.float32)
+    a[:, 2] = 0.4                                  # hold the arm up at the z clip (0.1): never touches the cube
+    steps = 0
+    done = np.zeros(n, bool)
+    while not done.all():
+        obs, r, d, su = s.step(a)
+        ret += np.where(done, 0, r)
+        done |= d.astype(bool)
+        steps += 1
+    assert steps == 501
+    assert (ret > -515.0).all() and (ret < -500.0).all(), ret
+    cube = s.get_state_f64(O.F_CUBE_POS)
+    assert np.allclose(cube[:, 2], -0.005, atol=2e-4)          # rests on the table: -0.025 + half side 0.02
+    assert np.abs(s.get_state_f64(O.F_CUBE_LINVEL)).max() < 1e-3
+
+
+def test_push_cube_moves_when_pushed(oracle):
+    """drive the flange into the cube: the cube must move away from the EE and end displaced on the table"""
+    O = oracle
+    s = O.OracleSim(O.default_config(O.TASK_PUSH, n_envs=1, seed=1))
+    s.reset()
+    ee = s.obs[0, :3].copy()
+    start = np.array([ee[0] - 0.10, ee[1], 0.01], np.float32)      # 10 cm in front of where the EE will come down
+    s.set_state(O.F_CUBE_POS, start[None])
+    s.set_state(O.F_GOAL, np.array([[0.25, 0.25, 0.01]], np.float32))
+    for _ in range(60):                                             # descend
+        s.step(np.array([[0, 0, -0.4]], np.float32))
+    c0 = s.get_state_f64(O.F_CUBE_POS)[0].copy()
+    for _ in range(80):                                             # sweep -x through the cube
+        s.step(np.array([[-0.05, 0, -0.4]], np.float32))
+    c1 = s.get_state_f64(O.F_CUBE_POS)[0]
+    assert c1[0] < c0[0] - 0.03, (c0, c1)
+    assert abs(c1[2] + 0.005) < 2e-3

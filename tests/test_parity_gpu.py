@@ -1,0 +1,345 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (fp32 device vs fp64 oracle), stated where used:
+  * integer / index work (Philox draws, step counters, episode counters): bit-exact
+  * sampled goals / cube poses at reset: bit-exact (f32 arithmetic mirrored with explicit FMA on both sides)
+  * FK: |dpos| <= 1e-6 m
+  * one teacher-forced env step with equal IK iteration counts: |dee| <= 5e-6 m, |dq| <= 2e-4 rad,
+    |dreward| <= 1e-4 (reach, r = -10 d)
+  * whatever the iteration count: |dee| <= 1.2e-4 m (Bullet's own 1e-4 residual contract)
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+WS_LO = np.array([0.2, -0.3, 0.0])
+WS_HI = np.array([0.7, 0.3, 0.55])
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _pair(pkg, oracle, task, n, seed=0, **kw):
+    tid = {"reach": 0, "push": 1, "pick": 2, "kuka_reach": 3}[task]
+    env = pkg.ArmSimHandle(task, n_envs=n, seed=seed, **kw)
+    ora = oracle.OracleSim(oracle.default_config(tid, n_envs=n, seed=seed, **kw))
+    return env, ora
+
+
+def _sync_state(env, ora, L, O, fields):
+    """teacher forcing: copy the oracle's (f32-rounded) state into both sims"""
+    for f in fields:
+        v = ora.get_state(f)
+        ora.set_state(f, v)
+        env.set_state(f, v)
+
+
+# --------------------------------------------------------------------------------------------- FK
+@pytest.mark.parametrize("robot", ["kuka_iiwa", "diana_s1"])
+def test_fk_parity(pkg, oracle, torch_cuda, robot):
+    env = pkg.ArmSimHandle("reach", n_envs=1, robot=robot)
+    rng = np.random.default_rng(0)
+    q = rng.uniform(-2.0, 2.0, (512, 7)).astype(np.float32)
+    pos, rot = env.fk(q)
+    rid = 0 if robot == "kuka_iiwa" else 1
+    for i in range(512):
+        p, R, _, _ = oracle.fk(q[i].astype(np.float64), rid)
+        assert np.abs(pos[i] - p).max() <= 1e-6
+        assert np.abs(rot[i] - R).max() <= 2e-6
+    env.close()
+
+
+def test_fk_golden_main_py_106(pkg, torch_cuda):
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ee_init_main_py.json")))
+    env = pkg.ArmSimHandle("reach", n_envs=1)
+    pos, _ = env.fk(np.array(g["init_joint_positions"], np.float32))
+    assert np.abs(pos[0] - np.array(g["ee"])).max() <= 2e-7
+    env.close()
+
+
+# --------------------------------------------------------------------------------------------- reset
+@pytest.mark.parametrize("task", ["reach", "kuka_reach", "push", "pick"])
+@pytest.mark.parametrize("n", [1, 129, 1000])
+def test_reset_bit_exact(pkg, oracle, torch_cuda, task, n):
+    L, O = pkg._lib, oracle
+    env, ora = _pair(pkg, oracle, task, n, seed=1234, env_id_offset=77)
+    for episode in range(3):
+        assert np.array_equal(env.get_state(L.F_GOAL), ora.get_state(O.F_GOAL))          # sampled targets: bit-exact
+        assert np.array_equal(env.get_state(L.F_EPISODE), ora.get_state(O.F_EPISODE))
+        assert np.array_equal(env.get_state(L.F_STEP), ora.get_state(O.F_STEP))
+        assert np.array_equal(env.get_state(L.F_Q), ora.get_state(O.F_Q))
+        if task in ("push", "pick"):
+            # x, y sampled bit-exact; z has taken one simulated step of free fall (reset's stepSimulation)
+            cg, co = env.get_state(L.F_CUBE_POS), ora.get_state(O.F_CUBE_POS)
+            assert np.array_equal(cg[:, :2], co[:, :2])
+            assert np.abs(cg[:, 2] - co[:, 2]).max() <= 1e-7
+            assert np.abs(env.get_state(L.F_CUBE_QUAT) - ora.get_state(O.F_CUBE_QUAT)).max() <= 2e-7
+        og = env.reset_host()
+        oo = ora.reset()
+        assert np.abs(og - oo).max() <= 2e-7
+    env.close()
+
+
+def test_reset_is_shard_invariant(pkg, torch_cuda):
+    """env g of a 2-rank job == env g of a 1-rank job (Philox keyed by the GLOBAL env id)"""
+    L = pkg._lib
+    whole = pkg.ArmSimHandle("reach", n_envs=256, seed=9)
+    lo = pkg.ArmSimHandle("reach", n_envs=128, seed=9, env_id_offset=0)
+    hi = pkg.ArmSimHandle("reach", n_envs=128, seed=9, env_id_offset=128)
+    g = whole.get_state(L.F_GOAL)
+    assert np.array_equal(g[:128], lo.get_state(L.F_GOAL)) and np.array_equal(g[128:], hi.get_state(L.F_GOAL))
+
+
+def test_masked_reset(pkg, torch_cuda):
+    L = pkg._lib
+    env = pkg.ArmSimHandle("reach", n_envs=64, seed=2)
+    g0 = env.get_state(L.F_GOAL).copy()
+    mask = np.zeros(64, np.uint8)
+    mask[::3] = 1
+    obs_in = np.full((64, 6), -7.0, np.float32)
+    obs = env.reset_host(mask, obs_in)
+    g1 = env.get_state(L.F_GOAL)
+    assert (g1[mask == 0] == g0[mask == 0]).all() and (g1[mask == 1] != g0[mask == 1]).any(axis=1).all()
+    assert (obs[mask == 0] == -7.0).all() and (obs[mask == 1, 3:] == g1[mask == 1]).all()
+    assert list(env.get_state(L.F_EPISODE)) == [2 if m else 1 for m in mask]
+
+
+# --------------------------------------------------------------------------------------------- step (teacher-forced)
+def _rollout_states(oracle, task_id, n, steps, seed):
+    """states visited by the oracle under random actions: realistic (q, goal) pairs for teacher forcing"""
+    ora = oracle.OracleSim(oracle.default_config(task_id, n_envs=n, seed=seed))
+    rng = np.random.default_rng(seed)
+    for _ in range(steps):
+        ora.step(rng.uniform(-0.7, 0.7, (n, 3)).astype(np.float32))
+    return ora, rng
+
+
+@pytest.mark.parametrize("task,tid", [("reach", 0), ("kuka_reach", 3)])
+def test_step_teacher_forced(pkg, oracle, torch_cuda, task, tid):
+    L, O = pkg._lib, oracle
+    n = 2048
+    ora, rng = _rollout_states(oracle, tid, n, 7, seed=3)
+    env = pkg.ArmSimHandle(task, n_envs=n, seed=3)
+    n_same = n_tot = 0
+    for k in range(12):
+        _sync_state(env, ora, L, O, [O.F_GOAL, O.F_STEP, O.F_Q])
+        scale = 0.7 if k % 3 else 2.0           # also exercise moves beyond the policy's range
+        a = rng.uniform(-scale, scale, (n, 3)).astype(np.float32)
+        og, rg, dg, sg = env.step_host(a)
+        oo, ro, do, so = ora.step(a)
+        same = env.get_state(L.F_IK_ITERS) == ora.get_state(O.F_IK_ITERS)
+        n_same += same.sum(); n_tot += n
+        err = np.abs(og[:, :3] - oo[:, :3]).max(axis=1)
+        assert err[same].max() <= 5e-6, err[same].max()
+        assert err.max() <= 1.2e-4
+        assert np.abs(env.get_state(L.F_Q) - ora.get_state(O.F_Q))[same].max() <= 2e-4
+        if task == "reach":
+            assert np.array_equal(og[:, 3:], oo[:, 3:])                       # goal echoed bit-exact
+            dist = np.linalg.norm(oo[:, :3].astype(np.float64) - oo[:, 3:], axis=1)
+            clear = same & (np.abs(dist - 0.01) > 1e-5)                      # away from the success threshold
+            assert np.array_equal(dg[clear], do[clear]) and np.array_equal(sg[clear], so[clear])
+            assert np.abs(rg - ro)[clear].max() <= 1e-4
+        else:
+            clear = same & (np.abs(np.linalg.norm(oo - ora.get_state(O.F_GOAL), axis=1) - 0.1) > 1e-5) \
+                & (np.abs(oo - WS_LO).min(axis=1) > 1e-5) & (np.abs(oo - WS_HI).min(axis=1) > 1e-5)
+            assert np.array_equal(dg[clear], do[clear]) and np.array_equal(rg[clear], ro[clear].astype(np.float32))
+        assert np.array_equal(env.get_state(L.F_STEP), ora.get_state(O.F_STEP))
+    assert n_same / n_tot > 0.98, n_same / n_tot
+    env.close()
+
+
+def test_reach_workspace_clip_and_corners(pkg, oracle, torch_cuda):
+    """targets outside the box are clipped (rl_reach_env.py:239-242); worst-case IK near the workspace corners"""
+    L, O = pkg._lib, oracle
+    n = 512
+    env, ora = _pair(pkg, oracle, "reach", n, seed=4)
+    rng = np.random.default_rng(4)
+    corners = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], np.float32)
+    a = corners[rng.integers(0, 8, n)] * 3.0
+    for k in range(40):
+        _sync_state(env, ora, L, O, [O.F_Q])
+        og, rg, dg, sg = env.step_host(a)
+        oo, ro, do, so = ora.step(a)
+        same = env.get_state(L.F_IK_ITERS) == ora.get_state(O.F_IK_ITERS)
+        assert np.abs(og[:, :3] - oo[:, :3])[same].max() <= 5e-6
+        assert (og[:, :3] >= WS_LO - 1.5e-4).all() and (og[:, :3] <= WS_HI + 1.5e-4).all()
+    # every env has been driven into its corner
+    tgt = np.where(a > 0, WS_HI, WS_LO)
+    assert np.abs(og[:, :3] - tgt).max() <= 1.5e-4
+
+
+def test_reach_truth_table_on_device(pkg, oracle, torch_cuda):
+    """same injected cases as the oracle's truth table (timeout / success / far / success+timeout)"""
+    L = pkg._lib
+    env = pkg.ArmSimHandle("reach", n_envs=4)
+    ee0 = env.reset_host()[0, :3].astype(np.float64)
+    goals = np.tile(ee0, (4, 1))
+    goals[0] += [0.003, 0, 0]; goals[1] += [0.2, 0, 0]; goals[2] += [0.2, 0, 0]; goals[3] += [0.003, 0, 0]
+    env.set_state(L.F_GOAL, goals.astype(np.float32))
+    env.set_state(L.F_STEP, np.array([0, 0, 500, 500], np.int32))
+    obs, r, d, su = env.step_host(np.zeros((4, 3), np.float32))
+    dist = np.linalg.norm(obs[:, :3].astype(np.float64) - obs[:, 3:], axis=1)
+    assert list(d) == [1, 0, 1, 1] and list(su) == [1, 0, 0, 0] and r[0] == 0.0
+    assert np.allclose(r[1:], -10 * dist[1:], atol=1e-5)
+    assert list(env.get_state(L.F_STEP)) == [1, 1, 501, 501]
+    obs2, r2, d2, _ = env.step_host(np.ones((4, 3), np.float32))       # finished envs wait for reset
+    assert list(d2) == [1, 0, 1, 1] and r2[0] == 0 and np.array_equal(obs2[0], obs[0])
+    env.close()
+
+
+def test_free_running_episode(pkg, oracle, torch_cuda):
+    """501 steps without teacher forcing: the fp32 trajectory may leave the fp64 one only through IK iteration-count
+    flips at the 1e-4 residual threshold (each worth <= 1e-4 m)"""
+    L, O = pkg._lib, oracle
+    n = 256
+    env, ora = _pair(pkg, oracle, "reach", n, seed=6)
+    far = np.tile([0.2, -0.3, 0.0], (n, 1)).astype(np.float32)
+    env.set_state(L.F_GOAL, far); ora.set_state(O.F_GOAL, far)
+    rng = np.random.default_rng(6)
+    flips = np.zeros(n)
+    for k in range(501):
+        a = rng.uniform(-0.7, 0.7, (n, 3)).astype(np.float32)
+        a[:, 0] += 0.3                                   # drift away from the far goal so nobody succeeds
+        og, rg, dg, sg = env.step_host(a)
+        oo, ro, do, so = ora.step(a)
+        flips += env.get_state(L.F_IK_ITERS) != ora.get_state(O.F_IK_ITERS)
+        assert np.array_equal(dg, do)
+    err = np.abs(og[:, :3] - oo[:, :3]).max(axis=1)
+    assert dg.all() and not sg.any()                      # everyone timed out at step 501
+    assert (err <= 2e-5 + 1.2e-4 * flips).all(), (err.max(), flips.max())
+    assert np.median(err) <= 2e-5
+    env.close()
+
+
+# --------------------------------------------------------------------------------------------- push / pick
+@pytest.mark.parametrize("task,tid", [("push", 1), ("pick", 2)])
+def test_cube_tasks_teacher_forced(pkg, oracle, torch_cuda, task, tid):
+    L, O = pkg._lib, oracle
+    n = 1024
+    env, ora = _pair(pkg, oracle, task, n, seed=8)
+    rng = np.random.default_rng(8)
+    fields = [O.F_Q, O.F_CUBE_POS, O.F_CUBE_QUAT, O.F_CUBE_LINVEL, O.F_CUBE_ANGVEL, O.F_LAST_DIST, O.F_GRIP]
+    # bring half of the arms down onto their cubes so that contacts are exercised
+    env.reset_host()
+    ora.reset()
+    for k in range(80):
+        _sync_state(env, ora, L, O, fields + [O.F_GOAL])
+        ee = ora.obs[:, :3]
+        cube = ora.get_state(O.F_CUBE_POS)
+        want = cube.copy()
+        want[:, 2] += 0.03 if task == "push" else 0.257 + 0.01
+        a = np.clip((want - ee) / 0.08, -0.4, 0.4).astype(np.float32)
+        a[n // 2:] = rng.uniform(-0.4, 0.4, (n - n // 2, 3)).astype(np.float32)
+        a += rng.normal(0, 0.05, a.shape).astype(np.float32)
+        og, rg, dg, sg = env.step_host(a)
+        oo, ro, do, so = ora.step(a)
+        same = env.get_state(L.F_IK_ITERS) == ora.get_state(O.F_IK_ITERS)
+        assert np.abs(og[:, :3] - oo[:, :3])[same].max() <= 5e-6
+        gg, go = env.get_state(L.F_GRIP), ora.get_state(O.F_GRIP)
+        ok = same & (gg == go)
+        assert ok.mean() > 0.97
+        # one cube step from identical state: positions to 2e-5 m (10 PGS sweeps in fp32 vs fp64)
+        assert np.abs(og[:, 3:6] - oo[:, 3:6])[ok].max() <= 2e-5, np.abs(og[:, 3:6] - oo[:, 3:6])[ok].max()
+        assert np.array_equal(og[:, 6:], oo[:, 6:])
+        assert np.abs(env.get_state(L.F_CUBE_LINVEL) - ora.get_state(O.F_CUBE_LINVEL))[ok].max() <= 5e-3
+        dist = np.linalg.norm(oo[:, 3:6] - oo[:, 6:], axis=1)
+        clear = ok & (np.abs(dist - 0.05) > 1e-4)
+        assert np.array_equal(dg[clear], do[clear]) and np.array_equal(sg[clear], so[clear])
+    if task == "pick":
+        assert (ora.get_state(O.F_GRIP) > 0).any()          # some grippers did close on their cube
+    env.close()
+
+
+def test_push_untouched_return_on_device(pkg, torch_cuda):
+    """known answer: untouched-cube episode return, see tests/test_oracle_golden.py"""
+    L = pkg._lib
+    n = 64
+    env = pkg.ArmSimHandle("push", n_envs=n, seed=5)
+    env.reset_host()
+    a = np.zeros((n, 3), np.float32)
+    a[:, 2] = 0.4
+    ret = np.zeros(n)
+    done = np.zeros(n, bool)
+    steps = 0
+    while not done.all():
+        o, r, d, s = env.step_host(a)
+        ret += np.where(done, 0, r)
+        done |= d.astype(bool)
+        steps += 1
+    assert steps == 501 and (ret > -515).all() and (ret < -500).all(), ret
+    assert np.allclose(env.get_state(L.F_CUBE_POS)[:, 2], -0.005, atol=3e-4)
+    env.close()
+
+
+# --------------------------------------------------------------------------------------------- API paths
+def test_device_path_equals_host_path(pkg, torch_cuda):
+    torch = torch_cuda
+    n = 777                                                   # ragged: not a multiple of the 128-thread block
+    a = np.random.default_rng(1).uniform(-0.7, 0.7, (n, 3)).astype(np.float32)
+    h = pkg.ArmSimHandle("reach", n_envs=n, seed=3)
+    e = pkg.BatchedArmEnv("reach", n_envs=n, seed=3, device="cuda:0")
+    for _ in range(5):
+        oh, rh, dh, sh = h.step_host(a)
+        od, rd, dd, sd = e.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(oh, od.cpu().numpy()) and np.array_equal(rh, rd.cpu().numpy())
+        assert np.array_equal(dh, dd.cpu().numpy()) and np.array_equal(sh, sd.cpu().numpy())
+    assert e.launch_count == 1 + 5 and h.launch_count == 1 + 5     # create's reset + one launch per step
+    h.close(); e.close()
+
+
+def test_auto_reset_full_size(pkg, torch_cuda):
+    """BASELINE config: N = 4096, > 1 episode with in-kernel auto-reset; size-independent properties"""
+    torch = torch_cuda
+    L = pkg._lib
+    n = 4096
+    env = pkg.BatchedArmEnv("reach", n_envs=n, seed=0, auto_reset=True, device="cuda:0")
+    obs = env.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ndone = torch.zeros(n, dtype=torch.int64, device="cuda")
+    nsucc = 0
+    for k in range(600):
+        a = (torch.rand((n, 3), device="cuda", generator=g) * 1.4 - 0.7)
+        o, r, d, s = env.step(a)
+        ndone += d.long()
+        nsucc += int(s.sum())
+        assert bool((r <= 0).all())
+        if k == 500:
+            # every env has finished at least one episode by step 501 (timeout :299) and restarted
+            assert int((ndone >= 1).sum()) == n
+    ee = env.obs[:, :3].cpu().numpy()
+    assert (ee >= WS_LO - 1.5e-4).all() and (ee <= WS_HI + 1.5e-4).all()
+    steps = env.get_state(L.F_STEP)
+    ep = env.get_state(L.F_EPISODE)
+    assert steps.max() <= 500 and (ep >= 3).all()         # create + reset + >= 1 auto-reset
+    assert env.launch_count == 2 + 600
+    env.close()
+
+
+@pytest.mark.parametrize("name,odim,dtype", [("RLReachEnv", 6, np.float32), ("RLPushEnv", 9, np.float64),
+                                              ("RLPickEnv", 9, np.float64), ("KukaReachEnv", 3, np.float32)])
+def test_drop_in_env_classes(pkg, torch_cuda, name, odim, dtype):
+    """main.py:83-87,111-128 usage: construct by name, read spaces, reset, step until done"""
+    env = getattr(pkg.envs, name)(is_render=True, is_good_view=False)
+    assert env.action_space.shape[0] == 3 and float(env.action_space.high[0]) == pytest.approx(0.4)
+    obs = env.reset()
+    assert obs.shape == (odim,) and obs.dtype == dtype
+    assert np.abs(obs[:3] - [0.5320540070533752, -0.0011213874677196145, 0.4962984025478363]).max() < 1e-6   # main.py:106
+    done, n = False, 0
+    while not done and n < 30:
+        obs, reward, done, info = env.step(env.action_space.sample())
+        n += 1
+        assert obs.shape == (odim,) and isinstance(reward, float) and isinstance(done, bool)
+    if name == "RLReachEnv":
+        assert isinstance(info, bool)
+    elif name == "KukaReachEnv":
+        assert isinstance(info, float)
+    else:
+        assert set(info) == {"is_success"} and info["is_success"].dtype == np.float32
+    env.close()
