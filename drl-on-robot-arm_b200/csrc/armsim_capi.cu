@@ -53,6 +53,28 @@ static void rpy_to_mat(const double rpy[3], double R[9]) {
   R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
 }
 
+// FK(q) of the chain in fp64 on the host (used once per handle for the constant start-of-episode EE pose)
+template <class Model>
+static void host_fk(const Model& m, const double q[NJ], double p[3], double R[9]) {
+  auto mul = [](const double A[9], const double B[9], double Cm[9]) {
+    double Tm[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Tm[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    memcpy(Cm, Tm, sizeof(Tm));
+  };
+  rpy_to_mat(m.base_rpy, R);
+  for (int i = 0; i < 3; ++i) p[i] = m.base_xyz[i];
+  for (int j = 0; j < NJ; ++j) {
+    for (int i = 0; i < 3; ++i) p[i] += R[3 * i] * m.xyz[j][0] + R[3 * i + 1] * m.xyz[j][1] + R[3 * i + 2] * m.xyz[j][2];
+    double Rf[9];
+    rpy_to_mat(m.rpy[j], Rf);
+    mul(R, Rf, R);
+    const double cq = cos(q[j]), sq = sin(q[j]);
+    const double Rz[9] = {cq, -sq, 0, sq, cq, 0, 0, 0, 1};
+    mul(R, Rz, R);
+  }
+}
+
 template <class Model>
 static void fill_chain(const Model& m, ChainParams& c) {
   double R[9];
@@ -184,9 +206,10 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   s->cfg = *cfg;
   s->cfg.custom_chain = nullptr;
   s->n = cfg->n_envs;
-  if (cfg->robot == ARMSIM_ROBOT_KUKA_IIWA) fill_chain(ARMSIM_MODEL_KUKA_IIWA, s->chain);
-  else if (cfg->robot == ARMSIM_ROBOT_DIANA_S1) fill_chain(ARMSIM_MODEL_DIANA_S1, s->chain);
-  else if (cfg->robot == ARMSIM_ROBOT_CUSTOM && cfg->custom_chain) fill_chain(*cfg->custom_chain, s->chain);
+  double ee0[3], R0[9];
+  if (cfg->robot == ARMSIM_ROBOT_KUKA_IIWA) { fill_chain(ARMSIM_MODEL_KUKA_IIWA, s->chain); host_fk(ARMSIM_MODEL_KUKA_IIWA, cfg->init_q, ee0, R0); }
+  else if (cfg->robot == ARMSIM_ROBOT_DIANA_S1) { fill_chain(ARMSIM_MODEL_DIANA_S1, s->chain); host_fk(ARMSIM_MODEL_DIANA_S1, cfg->init_q, ee0, R0); }
+  else if (cfg->robot == ARMSIM_ROBOT_CUSTOM && cfg->custom_chain) { fill_chain(*cfg->custom_chain, s->chain); host_fk(*cfg->custom_chain, cfg->init_q, ee0, R0); }
   else { delete s; return fail(ARMSIM_E_INVALID, "armsim_create: bad robot %d (custom needs custom_chain)", cfg->robot); }
 
   TaskParams& T = s->task;
@@ -202,6 +225,8 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   }
   quat_from_euler(cfg->target_rpy, T.tquat);
   for (int j = 0; j < NJ; ++j) T.init_q[j] = (float)cfg->init_q[j];
+  for (int i = 0; i < 3; ++i) T.init_ee[i] = (float)ee0[i];
+  for (int i = 0; i < 9; ++i) T.init_R[i] = (float)R0[i];
   T.seed_lo = (uint32_t)cfg->seed; T.seed_hi = (uint32_t)(cfg->seed >> 32);
   T.gid_offset = cfg->env_id_offset;
   s->mapping = ARMSIM_MAP_LANE;

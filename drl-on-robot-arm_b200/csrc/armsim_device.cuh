@@ -26,6 +26,7 @@ struct TaskParams {
   float goal_lo[3], goal_span[3];
   float tquat[4];            // IK target orientation, xyzw
   float init_q[NJ];
+  float init_ee[3], init_R[9];   // FK(init_q) computed once on the host in fp64 (every episode starts there)
   uint32_t seed_lo, seed_hi;
   unsigned long long gid_offset;
 };
@@ -68,6 +69,29 @@ __device__ __forceinline__ void reset_uniforms(const TaskParams& T, unsigned lon
 }
 
 // ------------------------------------------------------------------------------------------------ kinematics
+// sin/cos for joint angles: branch-free Cody-Waite reduction by pi/2 (3 constants, exact for |x| < ~1e4; joint angles
+// are bounded by a few turns) + the Cephes single-precision minimax polynomials on [-pi/4, pi/4]; <= 1 ulp-ish
+// (max abs error ~6e-8), ~22 instructions and no slow path, unlike sincosf whose Payne-Hanek branch bloats the
+// unrolled FK code (I-cache) and adds divergence bookkeeping.
+__device__ __forceinline__ void sincos_bounded(float x, float& s, float& c) {
+  const float k = rintf(x * 0.63661977236758134f);
+  float r = fmaf(k, -1.5707962512969971f, x);
+  r = fmaf(k, -7.5497894158615964e-08f, r);
+  r = fmaf(k, -5.3903029534742384e-15f, r);
+  const int i = (int)k;
+  const float z = r * r;
+  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(z, ps, -1.6666654611e-1f);
+  ps = fmaf(ps * z, r, r);
+  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(z, pc, 4.166664568298827e-2f);
+  pc = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
+  const float ss = (i & 1) ? pc : ps;
+  const float cc = (i & 1) ? ps : pc;
+  s = (i & 2) ? -ss : ss;
+  c = ((i + 1) & 2) ? -cc : cc;
+}
+
 // FK of the 7-joint chain.  P[j] = origin of joint j (world), Z[j] = its axis (world); p, R = EE link frame.
 template <bool WANT_JAC>
 __device__ __forceinline__ void chain_fk(const ChainParams& C, const float (&q)[NJ], float (&p)[3], float (&R)[9],
@@ -92,7 +116,7 @@ __device__ __forceinline__ void chain_fk(const ChainParams& C, const float (&q)[
       for (int i = 0; i < 3; ++i) { P[j][i] = p[i]; Z[j][i] = M[3 * i + 2]; }
     }
     float s, c;
-    sincosf(q[j], &s, &c);
+    sincos_bounded(q[j], s, c);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       R[3 * i] = fmaf(M[3 * i + 1], s, M[3 * i] * c);
@@ -228,13 +252,50 @@ __device__ __forceinline__ void dls_update(const float (&p)[3], const float (&P)
   }
 }
 
-// calculateInverseKinematics as the reference calls it (rl_reach_env.py:244-250).
-// In/out: q, and the FK state (p, R, P, Z) which must be valid for q on entry and is valid for the returned q.
-__device__ __forceinline__ int ik_solve(const ChainParams& C, const TaskParams& T, const float (&tgt)[3], float (&q)[NJ],
-                                        float (&p)[3], float (&R)[9], float (&P)[NJ][3], float (&Z)[NJ][3]) {
-  int it = 0;
-  float diff = 1e30f;
-  while (it < T.ik_max_iters && diff > T.ik_residual) {
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// The kinematic core of Env.step with ONE forward-kinematics site in the instruction stream (code size matters: the
+// fully unrolled FK + DLS body must stay inside the 32 KB L1.5 instruction cache):
+//
+//   pass 0        : FK(q)  -> current EE (getLinkState, rl_reach_env.py:237); target = clip(ee + a*dv) (:239-242)
+//   pass 1..iters : DLS update (calculateInverseKinematics, :244-250), FK(q), residual check
+//   final pass    : only when the teleport does not take every joint (pick: joints 0..5, rl_pick_env.py:342) or the
+//                   optional joint-limit clamp is on: FK of the state actually written back
+//
+// frozen = true (env finished, waiting for reset) runs pass 0 only.  Returns the DLS iteration count.
+template <bool CLIP>
+__device__ __forceinline__ int servo_core(const ChainParams& C, const TaskParams& T, const float (&a)[3], bool frozen,
+                                          float (&q)[NJ], float (&p)[3], float (&R)[9]) {
+  float P[NJ][3], Z[NJ][3], tgt[3] = {0.f, 0.f, 0.f};
+  const float q6_old = q[NJ - 1];
+  const bool need_final = (T.napply < NJ) || T.clamp;
+  int it = 0, phase = 0;  // 0 = first FK, 1 = iterating, 2 = final FK done
+  for (;;) {
+    chain_fk<true>(C, q, p, R, P, Z);
+    if (phase == 2 || frozen) break;
+    bool converged;
+    if (phase == 0) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        tgt[i] = fmaf(a[i], T.dv, p[i]);
+        if (CLIP) tgt[i] = clampf(tgt[i], T.ws_lo[i], T.ws_hi[i]);
+      }
+      phase = 1;
+      converged = false;   // Bullet starts from diff = +inf: at least one update whenever max_iters > 0
+    } else {
+      const float d0 = tgt[0] - p[0], d1 = tgt[1] - p[1], d2 = tgt[2] - p[2];
+      converged = sqrtf(d0 * d0 + d1 * d1 + d2 * d2) <= T.ik_residual;
+    }
+    if (converged || it >= T.ik_max_iters) {
+      if (!need_final) break;
+      if (T.napply < NJ) q[NJ - 1] = q6_old;
+      if (T.clamp) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) q[j] = clampf(q[j], C.lower[j], C.upper[j]);
+      }
+      phase = 2;
+      continue;
+    }
     float e[6], er[3], dq[NJ];
     e[0] = tgt[0] - p[0]; e[1] = tgt[1] - p[1]; e[2] = tgt[2] - p[2];
     rot_error(T.tquat, R, er);
@@ -242,12 +303,7 @@ __device__ __forceinline__ int ik_solve(const ChainParams& C, const TaskParams& 
     dls_update(p, P, Z, e, T.ik_damping, dq);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) q[j] += dq[j];
-    chain_fk<true>(C, q, p, R, P, Z);
-    const float d0 = tgt[0] - p[0], d1 = tgt[1] - p[1], d2 = tgt[2] - p[2];
-    diff = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
     ++it;
   }
   return it;
 }
-
-__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }

@@ -93,8 +93,12 @@ __device__ __forceinline__ void reset_env(const ChainParams& C, const TaskParams
   S.done[e] = 0;
   S.ik_iters[e] = 0;
   S.episode[e] = (int)(ep + 1u);
-  float p[3], R[9], P[NJ][3], Z[NJ][3];
-  chain_fk<false>(C, q, p, R, P, Z);
+  // every episode starts at init_joint_positions: its EE pose is a constant (FK done once on the host, fp64)
+  float p[3], R[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) p[i] = T.init_ee[i];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = T.init_R[i];
   if constexpr (TaskTraits<TASK>::HAS_CUBE) {
     S.grip[e] = 0.f;
     cube::step(cb, p, R, TASK == ARMSIM_TASK_PICK, 0.f);   // p.stepSimulation() rl_push_env.py:242
@@ -120,30 +124,14 @@ __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams&
   cube::State cb;
   if constexpr (TaskTraits<TASK>::HAS_CUBE) load_cube(S, n, e, cb);
 
-  float p[3], R[9], P[NJ][3], Z[NJ][3];
-  if (!T.auto_reset && S.done[e]) {   // finished env waiting for reset: report its frozen state
-    chain_fk<false>(C, q, p, R, P, Z);
+  float p[3], R[9];
+  const bool frozen = !T.auto_reset && S.done[e];   // finished env waiting for reset: report its frozen state
+  const int its = servo_core<TASK != ARMSIM_TASK_KUKA_REACH>(C, T, a, frozen, q, p, R);
+  if (frozen) {
     make_obs<TASK>(p, goal, cb, o);
     r = 0.f; d = 1; su = 0;
     return;
   }
-  chain_fk<true>(C, q, p, R, P, Z);                               // current_pos = getLinkState(...)[4]  :237
-  float tgt[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    tgt[i] = fmaf(a[i], T.dv, p[i]);                              // :232-234, :239-242
-    if constexpr (TASK != ARMSIM_TASK_KUKA_REACH) tgt[i] = clampf(tgt[i], T.ws_lo[i], T.ws_hi[i]);
-  }
-  const float q6_old = q[NJ - 1];
-  const int its = ik_solve(C, T, tgt, q, p, R, P, Z);             // :244-250
-  bool refk = false;
-  if (T.napply < NJ) { q[NJ - 1] = q6_old; refk = true; }         // rl_pick_env.py:342 only joints 0..5 are teleported
-  if (T.clamp) {
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) q[j] = clampf(q[j], C.lower[j], C.upper[j]);
-    refk = true;
-  }
-  if (refk) chain_fk<false>(C, q, p, R, P, Z);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) S.q[j * n + e] = q[j];             // resetJointState :252-257
   S.ik_iters[e] = its;

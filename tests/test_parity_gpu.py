@@ -134,11 +134,13 @@ def test_step_teacher_forced(pkg, oracle, torch_cuda, task, tid):
         a = rng.uniform(-scale, scale, (n, 3)).astype(np.float32)
         og, rg, dg, sg = env.step_host(a)
         oo, ro, do, so = ora.step(a)
-        same = env.get_state(L.F_IK_ITERS) == ora.get_state(O.F_IK_ITERS)
+        it_g, it_o = env.get_state(L.F_IK_ITERS), ora.get_state(O.F_IK_ITERS)
+        conv = (it_o < 20) & (it_g < 20)          # Bullet gives no guarantee once the 20-iteration cap is hit
+        same = (it_g == it_o) & conv
         n_same += same.sum(); n_tot += n
         err = np.abs(og[:, :3] - oo[:, :3]).max(axis=1)
         assert err[same].max() <= 5e-6, err[same].max()
-        assert err.max() <= 1.2e-4
+        assert err[conv].max() <= 1.2e-4
         assert np.abs(env.get_state(L.F_Q) - ora.get_state(O.F_Q))[same].max() <= 2e-4
         if task == "reach":
             assert np.array_equal(og[:, 3:], oo[:, 3:])                       # goal echoed bit-exact
@@ -240,15 +242,25 @@ def test_cube_tasks_teacher_forced(pkg, oracle, torch_cuda, task, tid):
         a += rng.normal(0, 0.05, a.shape).astype(np.float32)
         og, rg, dg, sg = env.step_host(a)
         oo, ro, do, so = ora.step(a)
-        same = env.get_state(L.F_IK_ITERS) == ora.get_state(O.F_IK_ITERS)
+        it_g, it_o = env.get_state(L.F_IK_ITERS), ora.get_state(O.F_IK_ITERS)
+        # pick never teleports joint 7 (rl_pick_env.py:342), so every IK call starts 90 deg off in yaw and a few
+        # envs run into Bullet's 20-iteration cap without converging: no parity claim for those
+        same = (it_g == it_o) & (it_o < 20)
         assert np.abs(og[:, :3] - oo[:, :3])[same].max() <= 5e-6
         gg, go = env.get_state(L.F_GRIP), ora.get_state(O.F_GRIP)
         ok = same & (gg == go)
         assert ok.mean() > 0.97
-        # one cube step from identical state: positions to 2e-5 m (10 PGS sweeps in fp32 vs fp64)
-        assert np.abs(og[:, 3:6] - oo[:, 3:6])[ok].max() <= 2e-5, np.abs(og[:, 3:6] - oo[:, 3:6])[ok].max()
+        # one cube step from identical state: positions to 5e-5 m (10 PGS sweeps in fp32 vs fp64, recovery speeds up to ~2 m/s); a HELD cube sits
+        # at the grasp point 0.257 m down the tool axis, so its position inherits the EE orientation difference
+        # (<= 4e-4 rad between fp32 and fp64 IK paths) times that lever arm: 1e-4 m
+        cerr = np.abs(og[:, 3:6] - oo[:, 3:6]).max(axis=1)
+        held = go >= 1.5
+        assert cerr[ok & ~held].max() <= 5e-5, (k, cerr[ok & ~held].max())
+        if (ok & held).any():
+            assert cerr[ok & held].max() <= 1e-4, (k, cerr[ok & held].max())
         assert np.array_equal(og[:, 6:], oo[:, 6:])
-        assert np.abs(env.get_state(L.F_CUBE_LINVEL) - ora.get_state(O.F_CUBE_LINVEL))[ok].max() <= 5e-3
+        verr = np.abs(env.get_state(L.F_CUBE_LINVEL) - ora.get_state(O.F_CUBE_LINVEL)).max(axis=1)
+        assert verr[ok].max() <= 5e-3, (k, verr[ok].max())
         dist = np.linalg.norm(oo[:, 3:6] - oo[:, 6:], axis=1)
         clear = ok & (np.abs(dist - 0.05) > 1e-4)
         assert np.array_equal(dg[clear], do[clear]) and np.array_equal(sg[clear], so[clear])

@@ -1,0 +1,16 @@
+"""Tiny driver for ncu: eager (non-graph) launches of the fused step kernel.
+   python tools/profile_step.py <task> <n_envs> <pool> <steps>"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import drl_on_robot_arm_b200 as pkg
+
+task, n, pool, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+envs = [pkg.BatchedArmEnv(task, n_envs=n, device="cuda:0", seed=0, auto_reset=True, env_id_offset=b * n) for b in range(pool)]
+acts = torch.rand((pool, n, 3), device="cuda") * 1.4 - 0.7
+if task != "reach":
+    acts *= 0.4 / 0.7
+for k in range(steps):
+    envs[k % pool].step(acts[k % pool])
+torch.cuda.synchronize()
+print("done", task, n, pool, steps)
