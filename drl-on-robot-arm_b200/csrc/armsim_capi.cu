@@ -170,14 +170,29 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
   return ARMSIM_OK;
 }
 
+// kernels are instantiated per (task, robot): the built-in robots use the generated straight-line FK, custom chains
+// the parameter-driven one
+#define ARMSIM_STEP_CASE(TASK, ROBOT)                                                                           \
+  case (TASK) * 4 + (ROBOT):                                                                                    \
+    step_lane_kernel<TASK, ROBOT><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su);        \
+    break;
+
 static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st) {
   const int grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
-  switch (s->cfg.task) {
-    case ARMSIM_TASK_REACH: step_lane_kernel<ARMSIM_TASK_REACH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su); break;
-    case ARMSIM_TASK_PUSH: step_lane_kernel<ARMSIM_TASK_PUSH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su); break;
-    case ARMSIM_TASK_PICK: step_lane_kernel<ARMSIM_TASK_PICK><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su); break;
-    case ARMSIM_TASK_KUKA_REACH: step_lane_kernel<ARMSIM_TASK_KUKA_REACH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su); break;
-    default: return fail(ARMSIM_E_INVALID, "bad task");
+  switch (s->cfg.task * 4 + s->cfg.robot) {
+    ARMSIM_STEP_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_KUKA_IIWA)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_DIANA_S1)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_CUSTOM)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_PUSH, ARMSIM_ROBOT_KUKA_IIWA)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_PUSH, ARMSIM_ROBOT_DIANA_S1)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_PUSH, ARMSIM_ROBOT_CUSTOM)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_PICK, ARMSIM_ROBOT_KUKA_IIWA)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_PICK, ARMSIM_ROBOT_DIANA_S1)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_PICK, ARMSIM_ROBOT_CUSTOM)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_KUKA_IIWA)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_DIANA_S1)
+    ARMSIM_STEP_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_CUSTOM)
+    default: return fail(ARMSIM_E_INVALID, "bad task / robot");
   }
   s->launches += 1;
   CU(cudaGetLastError());
@@ -375,7 +390,10 @@ int armsim_fk_host(ArmSim* s, const float* q_host, int32_t n, float* pos_host, f
   CU(cudaMalloc((void**)&dp, (size_t)n * 3 * 4));
   CU(cudaMalloc((void**)&dr, (size_t)n * 9 * 4));
   cudaMemcpyAsync(dq, q_host, (size_t)n * 7 * 4, cudaMemcpyHostToDevice, s->stream);
-  fk_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->chain, n, dq, dp, rot_host ? dr : nullptr);
+  const int g = (n + 127) / 128;
+  if (s->cfg.robot == ARMSIM_ROBOT_KUKA_IIWA) fk_kernel<ARMSIM_ROBOT_KUKA_IIWA><<<g, 128, 0, s->stream>>>(s->chain, n, dq, dp, rot_host ? dr : nullptr);
+  else if (s->cfg.robot == ARMSIM_ROBOT_DIANA_S1) fk_kernel<ARMSIM_ROBOT_DIANA_S1><<<g, 128, 0, s->stream>>>(s->chain, n, dq, dp, rot_host ? dr : nullptr);
+  else fk_kernel<ARMSIM_ROBOT_CUSTOM><<<g, 128, 0, s->stream>>>(s->chain, n, dq, dp, rot_host ? dr : nullptr);
   s->launches += 1;
   cudaMemcpyAsync(pos_host, dp, (size_t)n * 3 * 4, cudaMemcpyDeviceToHost, s->stream);
   if (rot_host) cudaMemcpyAsync(rot_host, dr, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, s->stream);

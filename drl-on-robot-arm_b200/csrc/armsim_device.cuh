@@ -252,6 +252,8 @@ __device__ __forceinline__ void dls_update(const float (&p)[3], const float (&P)
   }
 }
 
+#include "fk_generated.cuh"
+
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 // The kinematic core of Env.step with ONE forward-kinematics site in the instruction stream (code size matters: the
@@ -263,7 +265,7 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fm
 //                   optional joint-limit clamp is on: FK of the state actually written back
 //
 // frozen = true (env finished, waiting for reset) runs pass 0 only.  Returns the DLS iteration count.
-template <bool CLIP>
+template <int ROBOT, bool CLIP>
 __device__ __forceinline__ int servo_core(const ChainParams& C, const TaskParams& T, const float (&a)[3], bool frozen,
                                           float (&q)[NJ], float (&p)[3], float (&R)[9]) {
   float P[NJ][3], Z[NJ][3], tgt[3] = {0.f, 0.f, 0.f};
@@ -271,7 +273,7 @@ __device__ __forceinline__ int servo_core(const ChainParams& C, const TaskParams
   const bool need_final = (T.napply < NJ) || T.clamp;
   int it = 0, phase = 0;  // 0 = first FK, 1 = iterating, 2 = final FK done
   for (;;) {
-    chain_fk<true>(C, q, p, R, P, Z);
+    RobotFK<ROBOT>::template run<true>(C, q, p, R, P, Z);
     if (phase == 2 || frozen) break;
     bool converged;
     if (phase == 0) {

@@ -110,7 +110,7 @@ __device__ __forceinline__ void reset_env(const ChainParams& C, const TaskParams
 }
 
 // Env.step() for one env.  Returns through o / r / d / su.
-template <int TASK>
+template <int TASK, int ROBOT>
 __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams& T, const StatePtrs& S, int e,
                                          const float (&a)[3], float (&o)[TaskTraits<TASK>::OBS], float& r, uint8_t& d,
                                          uint8_t& su) {
@@ -126,7 +126,7 @@ __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams&
 
   float p[3], R[9];
   const bool frozen = !T.auto_reset && S.done[e];   // finished env waiting for reset: report its frozen state
-  const int its = servo_core<TASK != ARMSIM_TASK_KUKA_REACH>(C, T, a, frozen, q, p, R);
+  const int its = servo_core<ROBOT, TASK != ARMSIM_TASK_KUKA_REACH>(C, T, a, frozen, q, p, R);
   if (frozen) {
     make_obs<TASK>(p, goal, cb, o);
     r = 0.f; d = 1; su = 0;
@@ -189,7 +189,7 @@ __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams&
   }
 }
 
-template <int TASK>
+template <int TASK, int ROBOT>
 __global__ void __launch_bounds__(LANE_BLOCK)
 step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T, const StatePtrs S,
                  const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
@@ -206,7 +206,7 @@ step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ 
     const float a[3] = {s_act[threadIdx.x * 3], s_act[threadIdx.x * 3 + 1], s_act[threadIdx.x * 3 + 2]};
     float o[OD], r;
     uint8_t d, su;
-    step_env<TASK>(C, T, S, e, a, o, r, d, su);
+    step_env<TASK, ROBOT>(C, T, S, e, a, o, r, d, su);
 #pragma unroll
     for (int k = 0; k < OD; ++k) s_obs[threadIdx.x * OD + k] = o[k];
     reward[e] = r;
@@ -234,6 +234,7 @@ reset_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__
 }
 
 // FK of a host-supplied batch (armsim_fk_host): q [n,7] row-major -> pos [n,3], rot [n,9]
+template <int ROBOT>
 __global__ void fk_kernel(const __grid_constant__ ChainParams C, int n, const float* __restrict__ qin, float* __restrict__ pos,
                           float* __restrict__ rot) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,7 +242,7 @@ __global__ void fk_kernel(const __grid_constant__ ChainParams C, int n, const fl
   float q[NJ], p[3], R[9], P[NJ][3], Z[NJ][3];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) q[j] = qin[(size_t)e * NJ + j];
-  chain_fk<false>(C, q, p, R, P, Z);
+  RobotFK<ROBOT>::template run<false>(C, q, p, R, P, Z);
 #pragma unroll
   for (int i = 0; i < 3; ++i) pos[(size_t)e * 3 + i] = p[i];
   if (rot) {

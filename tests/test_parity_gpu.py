@@ -157,6 +157,64 @@ def test_step_teacher_forced(pkg, oracle, torch_cuda, task, tid):
     env.close()
 
 
+def _kuka_chain(mod):
+    """the Kuka chain handed over as a CUSTOM chain (exercises the parameter-driven FK instead of the generated one)"""
+    import json, os
+    m = json.load(open(os.path.join(os.path.dirname(__file__), "..", "drl-on-robot-arm_b200", "robots", "kuka_iiwa.json")))
+    ch = mod.ArmsimChain()
+    for i in range(3):
+        ch.base_xyz[i] = m["base_xyz"][i]; ch.base_rpy[i] = m["base_rpy"][i]
+    for j, jt in enumerate(m["joints"]):
+        for i in range(3):
+            ch.xyz[j][i] = jt["xyz"][i]; ch.rpy[j][i] = jt["rpy"][i]; ch.com[j][i] = jt["com"][i]
+        for i in range(6):
+            ch.inertia[j][i] = jt["inertia"][i]
+        ch.lower[j], ch.upper[j], ch.effort[j] = jt["lower"], jt["upper"], jt["effort"]
+        ch.velocity[j], ch.damping[j], ch.mass[j] = jt["velocity"], jt["damping"], jt["mass"]
+    return ch
+
+
+@pytest.mark.parametrize("robot", ["diana_s1", "custom"])
+def test_step_other_robots(pkg, oracle, torch_cuda, robot):
+    """DianaS1 (generated FK from models/diana/DianaS1_robot.urdf) and a custom chain (generic FK) through the step"""
+    import ctypes as C
+    L, O = pkg._lib, oracle
+    n = 512
+    if robot == "custom":
+        env = pkg.ArmSimHandle("reach", n_envs=n, seed=2, chain=_kuka_chain(L))
+        och = _kuka_chain(O)
+        cfg = O.default_config(O.TASK_REACH, n_envs=n, seed=2, robot=O.ROBOT_CUSTOM)
+        cfg.custom_chain = C.pointer(och)
+        ora = O.OracleSim(cfg)
+        ref = pkg.ArmSimHandle("reach", n_envs=n, seed=2)            # built-in Kuka: must agree with the custom copy
+    else:
+        # a DianaS1 pose with the tool pointing down, inside the workspace box (found with the oracle IK)
+        q0 = [0.7387, 1.3985, 1.2382, 2.0372, -1.8803, -1.359, -0.2102]   # EE (0.5, 0, 0.4), tool down (oracle IK)
+        env = pkg.ArmSimHandle("reach", n_envs=n, seed=2, robot="diana_s1", init_q=q0)
+        ora = O.OracleSim(O.default_config(O.TASK_REACH, n_envs=n, seed=2, robot=O.ROBOT_DIANA, init_q=q0))
+        ref = None
+    og, oo = env.reset_host(), ora.reset()
+    assert np.abs(og - oo).max() <= 2e-7
+    rng = np.random.default_rng(2)
+    checked = 0
+    for k in range(10):
+        _sync_state(env, ora, L, O, [O.F_Q])
+        if ref is not None:
+            ref.set_state(L.F_Q, ora.get_state(O.F_Q))
+        a = rng.uniform(-0.7, 0.7, (n, 3)).astype(np.float32)
+        og, rg, dg, sg = env.step_host(a)
+        oo, ro, do, so = ora.step(a)
+        it_g, it_o = env.get_state(L.F_IK_ITERS), ora.get_state(O.F_IK_ITERS)
+        same = (it_g == it_o) & (it_o < 20)
+        checked += same.sum()
+        assert np.abs(og[:, :3] - oo[:, :3])[same].max() <= 5e-6
+        if ref is not None:
+            orf = ref.step_host(a)[0]
+            assert np.abs(orf[:, :3] - og[:, :3]).max() <= 2e-6      # generated FK vs generic FK, same fp32 algorithm
+    assert checked > 0.9 * 10 * n
+    env.close()
+
+
 def test_reach_workspace_clip_and_corners(pkg, oracle, torch_cuda):
     """targets outside the box are clipped (rl_reach_env.py:239-242); worst-case IK near the workspace corners"""
     L, O = pkg._lib, oracle
