@@ -276,16 +276,24 @@ def run_ours(args):
         ev1.record(stream)
     barrier()
     sec = ev0.elapsed_time(ev1) * 1e-3
-    # ---- timed region 2: end to end through the host-buffer C-ABI call, every step H2D + launch + D2H
+    # ---- timed region 2: end to end through the host-buffer C-ABI call.  Every step: the [N,3] f32 actions sit in
+    # pinned host memory, cross PCIe to the GPU, the fused kernel runs, obs/reward/done/success cross back into pinned
+    # host memory and the call returns only when they are readable there (then one value of the result is read).
     e2e_steps = min(steps, args.e2e_steps)
-    h_act = [actions[b].cpu().numpy() for b in range(min(pool, 16))]
-    outs = (np.empty((n, envs[0].obs_dim), np.float32), np.empty(n, np.float32), np.empty(n, np.uint8), np.empty(n, np.uint8))
-    for k in range(3):
-        envs[k % pool].step_host(h_act[k % len(h_act)], outs)
+    e2e_pool = min(pool, 64)
+    bufs = []
+    for b in range(e2e_pool):
+        hb = envs[b].host_buffers()
+        hb[0][:] = actions[b].cpu().numpy()
+        bufs.append(hb)
+    for k in range(max(warmup, 3) + e2e_pool):
+        envs[k % e2e_pool].step_pinned()
     barrier()
+    acc = 0.0
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        envs[k % pool].step_host(h_act[k % len(h_act)], outs)
+        rew = envs[k % e2e_pool].step_pinned()[1]
+        acc += float(rew[0])                                  # the step's result is consumed on the host
     torch.cuda.synchronize(dev)
     e2e_sec = time.perf_counter() - t0
     barrier()
@@ -324,7 +332,8 @@ def run_ours(args):
                          "note": "kernel is fp32-issue / launch-latency bound, not HBM bound (SURVEY 7): ~6 kFLOP of "
                                  "dependent fp32 per 118 B"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "ArmSimHandle.step_host -> armsim_step_host (numpy host buffers)"},
+                    "steps": e2e_steps, "api": "ArmSimHandle.step_pinned -> armsim_step_host on the handle's pinned host block "
+                           "(armsim_host_buffers): kernel reads actions / writes results over PCIe, doorbell completion"},
             "gpu_launches": steps,
             "clocks": clocks,
         }

@@ -23,6 +23,7 @@ EXPORTS = [
     "armsim_abi_version", "armsim_last_error", "armsim_default_config", "armsim_create", "armsim_destroy",
     "armsim_reset", "armsim_step", "armsim_step_host", "armsim_reset_host", "armsim_set_state", "armsim_get_state",
     "armsim_obs_dim", "armsim_action_dim", "armsim_n_envs", "armsim_mapping", "armsim_launch_count", "armsim_fk_host",
+    "armsim_host_buffers",
 ]
 
 
@@ -78,6 +79,7 @@ def lib():
     L.armsim_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.armsim_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.armsim_reset_host.argtypes = [vp, vp, vp]
+    L.armsim_host_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
     L.armsim_set_state.argtypes = [vp, i32, vp, C.c_size_t]
     L.armsim_get_state.argtypes = [vp, i32, vp, C.c_size_t]
     for f in ("armsim_obs_dim", "armsim_action_dim", "armsim_n_envs", "armsim_mapping"):

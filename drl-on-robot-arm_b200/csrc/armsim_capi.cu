@@ -39,9 +39,13 @@ struct ArmSim {
   StatePtrs S{};
   void* state_block = nullptr;   // one allocation holding every SoA field
   // *_host path: one pinned block + one device block, outputs contiguous so the D2H is a single copy
-  char* h_pin = nullptr;
-  char* d_io = nullptr;
+  char* h_pin = nullptr;         // mapped + portable pinned block: [actions | obs | reward | done | success | flag]
+  char* d_io = nullptr;          // device twin of the same layout (large batches: DMA copies instead of zero-copy)
   size_t off_obs = 0, off_reward = 0, off_done = 0, off_success = 0, out_bytes = 0, act_bytes = 0;
+  unsigned int* d_counter = nullptr;   // blocks-finished counter of the doorbell
+  volatile unsigned int* h_flag = nullptr;
+  unsigned int seq = 0;
+  bool zero_copy = true;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
 };
@@ -151,6 +155,7 @@ void armsim_destroy(ArmSim* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->state_block) cudaFree(s->state_block);
   if (s->d_io) cudaFree(s->d_io);
+  if (s->d_counter) cudaFree(s->d_counter);
   if (s->h_pin) cudaFreeHost(s->h_pin);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -174,10 +179,11 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
 // the parameter-driven one
 #define ARMSIM_STEP_CASE(TASK, ROBOT)                                                                           \
   case (TASK) * 4 + (ROBOT):                                                                                    \
-    step_lane_kernel<TASK, ROBOT><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su);        \
+    step_lane_kernel<TASK, ROBOT><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su, H);     \
     break;
 
-static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st) {
+static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st,
+                       const HostNotify H = HostNotify{nullptr, nullptr, 0u}) {
   const int grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
   switch (s->cfg.task * 4 + s->cfg.robot) {
     ARMSIM_STEP_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_KUKA_IIWA)
@@ -239,6 +245,11 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
     T.goal_lo[i] = (float)cfg->goal_lo[i]; T.goal_span[i] = (float)(cfg->goal_hi[i] - cfg->goal_lo[i]);
   }
   quat_from_euler(cfg->target_rpy, T.tquat);
+  {
+    double tRd[9];
+    rpy_to_mat(cfg->target_rpy, tRd);   // getQuaternionFromEuler = Rz(yaw) Ry(pitch) Rx(roll), the URDF rpy convention
+    for (int i = 0; i < 9; ++i) T.tR[i] = (float)tRd[i];
+  }
   for (int j = 0; j < NJ; ++j) T.init_q[j] = (float)cfg->init_q[j];
   for (int i = 0; i < 3; ++i) T.init_ee[i] = (float)ee0[i];
   for (int i = 0; i < 9; ++i) T.init_R[i] = (float)R0[i];
@@ -276,13 +287,20 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   s->off_done = s->off_reward + pad(n * 4);
   s->off_success = s->off_done + pad(n);
   s->out_bytes = s->off_success + pad(n);
+  // zero-copy (kernel reads actions from / writes results to mapped host memory, completion by doorbell) while the
+  // per-step payload is small enough for PCIe latency, not bandwidth, to dominate; DMA copies beyond that
+  s->zero_copy = n <= 65536;
   if (cudaMalloc((void**)&s->d_io, s->act_bytes + s->out_bytes) != cudaSuccess ||
-      cudaMallocHost((void**)&s->h_pin, s->act_bytes + s->out_bytes) != cudaSuccess ||
+      cudaMalloc((void**)&s->d_counter, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(s->d_counter, 0, sizeof(unsigned int)) != cudaSuccess ||
+      cudaHostAlloc((void**)&s->h_pin, s->act_bytes + s->out_bytes + 256, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
       cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     armsim_destroy(s);
     return fail(ARMSIM_E_NOMEM, "armsim_create: staging allocation failed");
   }
+  s->h_flag = (volatile unsigned int*)(s->h_pin + s->act_bytes + s->out_bytes);
+  *s->h_flag = 0;
   int rc = launch_reset(s, nullptr, nullptr, s->stream);
   if (rc == ARMSIM_OK && cudaStreamSynchronize(s->stream) != cudaSuccess) rc = fail(ARMSIM_E_CUDA, "armsim_create: initial reset failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (rc != ARMSIM_OK) { armsim_destroy(s); return rc; }
@@ -302,6 +320,33 @@ int armsim_step(ArmSim* s, const float* action_dev, float* obs_dev, float* rewar
   return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream);
 }
 
+// Wait for the kernel's doorbell.  Polls the mapped flag; every so often asks the driver whether the stream died so
+// a faulting kernel turns into an error code instead of a hang.
+static int wait_doorbell(ArmSim* s, unsigned int seq) {
+  for (unsigned long long spins = 1;; ++spins) {
+    if (*s->h_flag == seq) return ARMSIM_OK;
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 0xFFFFull) == 0) {
+      cudaError_t q = cudaStreamQuery(s->stream);
+      if (q == cudaSuccess) return *s->h_flag == seq ? ARMSIM_OK : fail(ARMSIM_E_CUDA, "armsim_step_host: kernel finished without ringing the doorbell");
+      if (q != cudaErrorNotReady) return fail(ARMSIM_E_CUDA, "armsim_step_host: %s", cudaGetErrorString(q));
+    }
+  }
+}
+
+int armsim_host_buffers(ArmSim* s, float** action, float** obs, float** reward, uint8_t** done, uint8_t** success) {
+  if (!s) return fail(ARMSIM_E_INVALID, "armsim_host_buffers: null handle");
+  char* h_out = s->h_pin + s->act_bytes;
+  if (action) *action = (float*)s->h_pin;
+  if (obs) *obs = (float*)(h_out + s->off_obs);
+  if (reward) *reward = (float*)(h_out + s->off_reward);
+  if (done) *done = (uint8_t*)(h_out + s->off_done);
+  if (success) *success = (uint8_t*)(h_out + s->off_success);
+  return ARMSIM_OK;
+}
+
 int armsim_step_host(ArmSim* s, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host,
                      uint8_t* success_host) {
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_host: null handle");
@@ -310,17 +355,28 @@ int armsim_step_host(ArmSim* s, const float* action_host, float* obs_host, float
   const size_t n = (size_t)s->n;
   char* h_out = s->h_pin + s->act_bytes;
   char* d_out = s->d_io + s->act_bytes;
-  memcpy(s->h_pin, action_host, n * s->act_dim * 4);
-  CU(cudaMemcpyAsync(s->d_io, s->h_pin, n * s->act_dim * 4, cudaMemcpyHostToDevice, s->stream));
-  int rc = launch_step(s, (const float*)s->d_io, (float*)(d_out + s->off_obs), (float*)(d_out + s->off_reward),
-                       (uint8_t*)(d_out + s->off_done), (uint8_t*)(d_out + s->off_success), s->stream);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(h_out, d_out, s->out_bytes, cudaMemcpyDeviceToHost, s->stream));
-  CU(cudaStreamSynchronize(s->stream));
-  memcpy(obs_host, h_out + s->off_obs, n * s->obs_dim * 4);
-  memcpy(reward_host, h_out + s->off_reward, n * 4);
-  memcpy(done_host, h_out + s->off_done, n);
-  memcpy(success_host, h_out + s->off_success, n);
+  // callers that work in the handle's own pinned block (armsim_host_buffers) skip the staging memcpys
+  if ((const char*)action_host != s->h_pin) memcpy(s->h_pin, action_host, n * s->act_dim * 4);
+  if (s->zero_copy) {
+    const unsigned int seq = ++s->seq ? s->seq : ++s->seq;   // never 0 (the flag's idle value)
+    HostNotify H{s->d_counter, (unsigned int*)s->h_flag, seq};
+    int rc = launch_step(s, (const float*)s->h_pin, (float*)(h_out + s->off_obs), (float*)(h_out + s->off_reward),
+                         (uint8_t*)(h_out + s->off_done), (uint8_t*)(h_out + s->off_success), s->stream, H);
+    if (rc) return rc;
+    rc = wait_doorbell(s, seq);
+    if (rc) return rc;
+  } else {
+    CU(cudaMemcpyAsync(s->d_io, s->h_pin, n * s->act_dim * 4, cudaMemcpyHostToDevice, s->stream));
+    int rc = launch_step(s, (const float*)s->d_io, (float*)(d_out + s->off_obs), (float*)(d_out + s->off_reward),
+                         (uint8_t*)(d_out + s->off_done), (uint8_t*)(d_out + s->off_success), s->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_out, d_out, s->out_bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  if ((char*)obs_host != h_out + s->off_obs) memcpy(obs_host, h_out + s->off_obs, n * s->obs_dim * 4);
+  if ((char*)reward_host != h_out + s->off_reward) memcpy(reward_host, h_out + s->off_reward, n * 4);
+  if ((char*)done_host != h_out + s->off_done) memcpy(done_host, h_out + s->off_done, n);
+  if ((char*)success_host != h_out + s->off_success) memcpy(success_host, h_out + s->off_success, n);
   return ARMSIM_OK;
 }
 

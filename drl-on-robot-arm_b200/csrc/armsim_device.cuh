@@ -25,6 +25,7 @@ struct TaskParams {
   float ws_lo[3], ws_hi[3];
   float goal_lo[3], goal_span[3];
   float tquat[4];            // IK target orientation, xyzw
+  float tR[9];               // the same orientation as a row-major rotation matrix
   float init_q[NJ];
   float init_ee[3], init_R[9];   // FK(init_q) computed once on the host in fp64 (every episode starts there)
   uint32_t seed_lo, seed_hi;
@@ -66,6 +67,35 @@ __device__ __forceinline__ void reset_uniforms(const TaskParams& T, unsigned lon
   philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), episode, block, T.seed_lo, T.seed_hi, r);
 #pragma unroll
   for (int i = 0; i < 4; ++i) u[i] = __fmul_rn((float)(r[i] >> 8), 5.9604644775390625e-08f);
+}
+
+
+// ------------------------------------------------------------------------------------------------ fast scalar math
+// Single-MUFU forms (<= 2 ulp) without the IEEE slow paths: sqrtf / fdiv expand into a fast path + a CALL to a
+// denormal / rounding fix-up routine, which splits basic blocks (less ILP for ptxas) and bloats the unrolled body.
+// The servo tolerates 1e-7 relative error everywhere these are used; the reset sampler, which must be bit-exact
+// with the oracle, keeps the _rn intrinsics.
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// atan2(s, c) for s >= 0 -> [0, pi].  Branch-free: a = min/max in [0,1], odd minimax polynomial (degree 17, fitted
+// with the a -> 0 slope pinned to 1; max abs error 7.4e-8 evaluated in fp32), then the two octant reflections.
+__device__ __forceinline__ float atan2_nonneg(float s, float c) {
+  const float ac = fabsf(c);
+  const float mx = fmaxf(s, ac), mn = fminf(s, ac);
+  const float a = mn * fast_rcp(fmaxf(mx, 1e-30f));
+  const float z = a * a;
+  float p = fmaf(z, 2.622258617e-03f, -1.513261348e-02f);
+  p = fmaf(z, p, 4.112202674e-02f);
+  p = fmaf(z, p, -7.366725057e-02f);
+  p = fmaf(z, p, 1.057394370e-01f);
+  p = fmaf(z, p, -1.418597847e-01f);
+  p = fmaf(z, p, 1.999039650e-01f);
+  p = fmaf(z, p, -3.333298564e-01f);
+  float r = fmaf(p * z, a, a);
+  r = (s > ac) ? 1.57079632679489662f - r : r;
+  return (c < 0.0f) ? 3.14159265358979324f - r : r;
 }
 
 // ------------------------------------------------------------------------------------------------ kinematics
@@ -156,7 +186,7 @@ __device__ __forceinline__ void mat_to_quat(const float (&m)[9], float (&q)[4]) 
 // Bullet (IKTrajectoryHelper::computeIK) forms it as 2*acos(w) * v/sqrt(1-w^2); for a unit quaternion that is
 // 2*atan2(|v|, w) * v/|v|, which is the form used here because it stays well-conditioned in fp32 when the error is
 // small (acos near 1 loses half the mantissa).
-__device__ __forceinline__ void rot_error(const float (&tq)[4], const float (&R)[9], float (&e)[3]) {
+__device__ __noinline__ void rot_error_quat(const float (&tq)[4], const float (&R)[9], float (&e)[3]) {
   float sq[4];
   mat_to_quat(R, sq);
   const float ix = -sq[0], iy = -sq[1], iz = -sq[2], iw = sq[3];
@@ -174,6 +204,36 @@ __device__ __forceinline__ void rot_error(const float (&tq)[4], const float (&R)
     k = ang / vn;
   }
   e[0] = k * dx; e[1] = k * dy; e[2] = k * dz;
+}
+
+
+// The same rotation vector from the error matrix E = R_target R^T without going through quaternions:
+//   vee(E - E^T)/2 = sin(theta) * axis,  (tr E - 1)/2 = cos(theta),  e = axis * theta = v * theta / |v|.
+// Straight-line (no Shepperd branches, which diverge lane by lane when the EE sits at the reference's target
+// orientation, trace = -1 with two equal diagonal maxima) and well conditioned for theta in [0, ~170 deg]; beyond
+// that sin(theta) -> 0 and the (cold) quaternion form above takes over.
+__device__ __forceinline__ void rot_error(const float (&tR)[9], const float (&tq)[4], const float (&R)[9], float (&e)[3]) {
+  // E[i][j] = row_i(tR) . row_j(R)
+  const float e21 = fmaf(tR[8], R[5], fmaf(tR[7], R[4], tR[6] * R[3]));
+  const float e12 = fmaf(tR[5], R[8], fmaf(tR[4], R[7], tR[3] * R[6]));
+  const float e02 = fmaf(tR[2], R[8], fmaf(tR[1], R[7], tR[0] * R[6]));
+  const float e20 = fmaf(tR[8], R[2], fmaf(tR[7], R[1], tR[6] * R[0]));
+  const float e10 = fmaf(tR[5], R[2], fmaf(tR[4], R[1], tR[3] * R[0]));
+  const float e01 = fmaf(tR[2], R[5], fmaf(tR[1], R[4], tR[0] * R[3]));
+  const float e00 = fmaf(tR[2], R[2], fmaf(tR[1], R[1], tR[0] * R[0]));
+  const float e11 = fmaf(tR[5], R[5], fmaf(tR[4], R[4], tR[3] * R[3]));
+  const float e22 = fmaf(tR[8], R[8], fmaf(tR[7], R[7], tR[6] * R[6]));
+  const float vx = 0.5f * (e21 - e12), vy = 0.5f * (e02 - e20), vz = 0.5f * (e10 - e01);
+  const float c = 0.5f * (e00 + e11 + e22 - 1.0f);
+  if (c < -0.98f) {            // within ~11 deg of a half turn: cold path
+    rot_error_quat(tq, R, e);
+    return;
+  }
+  const float s2 = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
+  const float s = fast_sqrt(s2);
+  // theta / sin(theta); -> 1 as theta -> 0 (s below 1e-4 rad: the series term s^2/6 is under fp32 resolution)
+  const float k = s < 1e-4f ? 1.0f : atan2_nonneg(s, c) * fast_rcp(s);
+  e[0] = k * vx; e[1] = k * vy; e[2] = k * vz;
 }
 
 // One damped-least-squares update  dq = J^T (J J^T + lambda I)^-1 e  -- algebraically identical to Bullet's
@@ -213,7 +273,7 @@ __device__ __forceinline__ void dls_update(const float (&p)[3], const float (&P)
       for (int m = 0; m < k; ++m) acc = fmaf(-A[i][m], A[k][m], acc);
       if (k == i) {
         acc = fmaxf(acc, 1e-20f);
-        inv[i] = rsqrtf(acc);
+        inv[i] = fast_rsqrt(acc);
         A[i][i] = acc * inv[i];
       } else {
         A[i][k] = acc * inv[k];
@@ -246,7 +306,7 @@ __device__ __forceinline__ void dls_update(const float (&p)[3], const float (&P)
   }
   const float max_angle = 0.78539816339744831f;  // BussIK MaxAngleDLS = 45 deg
   if (mx > max_angle) {
-    const float sc = max_angle / mx;
+    const float sc = max_angle * fast_rcp(mx);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) dq[j] *= sc;
   }
@@ -286,7 +346,7 @@ __device__ __forceinline__ int servo_core(const ChainParams& C, const TaskParams
       converged = false;   // Bullet starts from diff = +inf: at least one update whenever max_iters > 0
     } else {
       const float d0 = tgt[0] - p[0], d1 = tgt[1] - p[1], d2 = tgt[2] - p[2];
-      converged = sqrtf(d0 * d0 + d1 * d1 + d2 * d2) <= T.ik_residual;
+      converged = fast_sqrt(fmaf(d2, d2, fmaf(d1, d1, d0 * d0))) <= T.ik_residual;
     }
     if (converged || it >= T.ik_max_iters) {
       if (!need_final) break;
@@ -300,7 +360,7 @@ __device__ __forceinline__ int servo_core(const ChainParams& C, const TaskParams
     }
     float e[6], er[3], dq[NJ];
     e[0] = tgt[0] - p[0]; e[1] = tgt[1] - p[1]; e[2] = tgt[2] - p[2];
-    rot_error(T.tquat, R, er);
+    rot_error(T.tR, T.tquat, R, er);
     e[3] = er[0]; e[4] = er[1]; e[5] = er[2];
     dls_update(p, P, Z, e, T.ik_damping, dq);
 #pragma unroll

@@ -109,44 +109,70 @@ __device__ __forceinline__ void reset_env(const ChainParams& C, const TaskParams
   make_obs<TASK>(p, goal, cb, o);
 }
 
-// Env.step() for one env.  Returns through o / r / d / su.
-template <int TASK, int ROBOT>
-__device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams& T, const StatePtrs& S, int e,
-                                         const float (&a)[3], float (&o)[TaskTraits<TASK>::OBS], float& r, uint8_t& d,
-                                         uint8_t& su) {
-  const int n = T.n;
+// Per-env state of one step, held in registers between the load and the store phase.
+template <int TASK>
+struct EnvRegs {
   float q[NJ], goal[3];
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) q[j] = S.q[j * n + e];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) goal[i] = S.goal[i * n + e];
-  int stepc = S.step[e];
+  int stepc;
+  uint8_t latched;     // done flag latched by a previous step (auto_reset = 0)
   cube::State cb;
-  if constexpr (TaskTraits<TASK>::HAS_CUBE) load_cube(S, n, e, cb);
+  float last_dist, grip;
+};
+
+// Issue EVERY global load of the step back to back (one HBM round trip, not one per field).
+template <int TASK>
+__device__ __forceinline__ void load_env(const TaskParams& T, const StatePtrs& S, int e, EnvRegs<TASK>& E) {
+  const int n = T.n;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) E.q[j] = S.q[j * n + e];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) E.goal[i] = S.goal[i * n + e];
+  E.stepc = S.step[e];
+  E.latched = T.auto_reset ? (uint8_t)0 : S.done[e];
+  if constexpr (TaskTraits<TASK>::HAS_CUBE) {
+    load_cube(S, n, e, E.cb);
+    E.last_dist = S.last_dist[e];
+    E.grip = S.grip[e];
+  }
+}
+
+// Env.step() for one env on pre-loaded registers.  Returns through o / r / d / su; `live` = false lanes (padding of
+// the last warp) compute on a clone of the last env and store nothing.
+template <int TASK, int ROBOT>
+__device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams& T, const StatePtrs& S, int e, bool live,
+                                         EnvRegs<TASK>& E, const float (&a)[3], float (&o)[TaskTraits<TASK>::OBS],
+                                         float& r, uint8_t& d, uint8_t& su) {
+  const int n = T.n;
+  float (&q)[NJ] = E.q;
+  float (&goal)[3] = E.goal;
+  cube::State& cb = E.cb;
+  int stepc = E.stepc;
 
   float p[3], R[9];
-  const bool frozen = !T.auto_reset && S.done[e];   // finished env waiting for reset: report its frozen state
+  const bool frozen = E.latched != 0;               // finished env waiting for reset: report its frozen state
   const int its = servo_core<ROBOT, TASK != ARMSIM_TASK_KUKA_REACH>(C, T, a, frozen, q, p, R);
   if (frozen) {
     make_obs<TASK>(p, goal, cb, o);
     r = 0.f; d = 1; su = 0;
     return;
   }
+  if (live) {
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) S.q[j * n + e] = q[j];             // resetJointState :252-257
-  S.ik_iters[e] = its;
+    for (int j = 0; j < NJ; ++j) S.q[j * n + e] = q[j];           // resetJointState :252-257
+    S.ik_iters[e] = its;
+  }
   stepc += 1;                                                     // :264
 
   bool term = false, succ = false;
   if constexpr (TASK == ARMSIM_TASK_REACH) {
     const float d0 = p[0] - goal[0], d1 = p[1] - goal[1], d2 = p[2] - goal[2];
-    const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);       // :281
+    const float dist = fast_sqrt(fmaf(d2, d2, fmaf(d1, d1, d0 * d0)));   // :281
     if (stepc > T.max_steps) { r = -dist * 10.f; term = true; }  // :299-301
     else if (dist < T.reach_dis) { r = 0.f; term = true; succ = true; }  // :303-306
     else { r = -dist * 10.f; }                                    // :307-309
   } else if constexpr (TASK == ARMSIM_TASK_KUKA_REACH) {
     const float d0 = p[0] - goal[0], d1 = p[1] - goal[1], d2 = p[2] - goal[2];
-    const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    const float dist = fast_sqrt(fmaf(d2, d2, fmaf(d1, d1, d0 * d0)));
     const bool oob = p[0] < T.ws_lo[0] || p[0] > T.ws_hi[0] || p[1] < T.ws_lo[1] || p[1] > T.ws_hi[1] ||
                      p[2] < T.ws_lo[2] || p[2] > T.ws_hi[2];     // kuka_reach_env.py:276-278
     if (oob) { r = -1.f; term = true; }
@@ -155,7 +181,7 @@ __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams&
     else { r = 0.f; }
   } else {
     constexpr bool PICK = TASK == ARMSIM_TASK_PICK;
-    float grip = S.grip[e];
+    float grip = E.grip;
     cube::step(cb, p, R, PICK, grip);                             // p.stepSimulation() rl_push_env.py:349
     if constexpr (PICK) {
       if (grip < 0.5f && cube::gripper_distance(cb, p, R) < cube::CLOSE_DIST) {   // rl_pick_env.py:412-416
@@ -165,22 +191,23 @@ __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams&
         grip = sqrtf(h0 * h0 + h1 * h1 + h2 * h2) < cube::HOLD_DIST ? 2.f : 1.f;
       }
       cube::step(cb, p, R, PICK, grip);                           // second p.stepSimulation() :417
-      S.grip[e] = grip;
+      if (live) S.grip[e] = grip;
     }
     const float d0 = cb.pos[0] - goal[0], d1 = cb.pos[1] - goal[1], d2 = cb.pos[2] - goal[2];
     const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);       // rl_push_env.py:383 / :393
-    float test = dist - S.last_dist[e];                           // :385
+    float test = dist - E.last_dist;                              // :385
     if (fabsf(test) < 1e-5f) test = 0.01f;                        // :386-387
-    S.last_dist[e] = dist;
+    if (live) S.last_dist[e] = dist;
     if (stepc > T.max_steps) { r = -dist * 50.f; term = true; }   // :417-419
     else if (dist < 0.05f) { r = 100.f; term = true; }            // :421-423
     else { r = -test * 100.f; }                                   // :424-428
     succ = dist < T.reach_dis;                                    // _is_success :442-445
-    store_cube(S, n, e, cb);
+    if (live) store_cube(S, n, e, cb);
   }
-  S.step[e] = stepc;
   d = term ? 1 : 0;
   su = succ ? 1 : 0;
+  if (!live) { make_obs<TASK>(p, goal, cb, o); return; }
+  S.step[e] = stepc;
   if (term && T.auto_reset) {
     reset_env<TASK>(C, T, S, e, o);
   } else {
@@ -189,32 +216,82 @@ __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams&
   }
 }
 
+// Completion doorbell of the host-buffer path (armsim_step_host): when `flag` is non-null the kernel's outputs go
+// straight to mapped pinned host memory and the LAST block to finish publishes `seq` there, so the host learns of
+// completion by polling one cache line instead of paying a stream synchronise.
+struct HostNotify {
+  unsigned int* counter;   // device: blocks finished (self-resetting)
+  unsigned int* flag;      // mapped host memory
+  unsigned int seq;
+};
+
+__device__ __forceinline__ void notify_host(const HostNotify& H) {
+  if (H.flag == nullptr) return;
+  __threadfence_system();                 // this thread's output stores are visible to the host ...
+  __syncthreads();                        // ... for every thread of the block
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(H.counter, 1u) == gridDim.x - 1) {
+      *H.counter = 0;
+      __threadfence_system();
+      *(volatile unsigned int*)H.flag = H.seq;
+    }
+  }
+}
+
+// One launch = Env.step() of the whole batch.  Each warp owns 32 consecutive envs and is self-contained: it stages
+// its [32,3] action rows and [32,OBS] observation rows through its own slice of shared memory (row-major caller
+// layout <-> one-value-per-lane), ordered by __syncwarp only -- no block-wide barrier on the device path, so warps
+// never wait for each other's HBM latency.
 template <int TASK, int ROBOT>
 __global__ void __launch_bounds__(LANE_BLOCK)
 step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T, const StatePtrs S,
                  const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
-                 uint8_t* __restrict__ done, uint8_t* __restrict__ success) {
+                 uint8_t* __restrict__ done, uint8_t* __restrict__ success, const HostNotify H) {
   constexpr int OD = TaskTraits<TASK>::OBS;
-  __shared__ float s_act[LANE_BLOCK * 3];
-  __shared__ float s_obs[LANE_BLOCK * OD];
-  const int base = blockIdx.x * LANE_BLOCK;
-  const int cnt = min(LANE_BLOCK, T.n - base);
-  for (int i = threadIdx.x; i < cnt * 3; i += LANE_BLOCK) s_act[i] = action[(size_t)base * 3 + i];
-  __syncthreads();
-  const int e = base + threadIdx.x;
-  if (threadIdx.x < cnt) {
-    const float a[3] = {s_act[threadIdx.x * 3], s_act[threadIdx.x * 3 + 1], s_act[threadIdx.x * 3 + 2]};
+  constexpr int STAGE = 32 * (OD > 3 ? OD : 3);
+  __shared__ float s_io[LANE_BLOCK / 32][STAGE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wbase = blockIdx.x * LANE_BLOCK + warp * 32;
+  if (wbase < T.n) {
+    const int cnt = min(32, T.n - wbase);
+    const bool live = lane < cnt;
+    const int e = wbase + min(lane, cnt - 1);
+    float* st = s_io[warp];
+
+    float araw[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = k * 32 + lane;
+      araw[k] = i < cnt * 3 ? __ldg(action + (size_t)wbase * 3 + i) : 0.f;
+    }
+    EnvRegs<TASK> E;
+    load_env<TASK>(T, S, e, E);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) st[k * 32 + lane] = araw[k];
+    __syncwarp();
+    const int al = min(lane, cnt - 1) * 3;
+    const float a[3] = {st[al], st[al + 1], st[al + 2]};
+    __syncwarp();
+
     float o[OD], r;
     uint8_t d, su;
-    step_env<TASK, ROBOT>(C, T, S, e, a, o, r, d, su);
+    step_env<TASK, ROBOT>(C, T, S, e, live, E, a, o, r, d, su);
+    if (live) {
+      reward[e] = r;
+      done[e] = d;
+      success[e] = su;
+    }
 #pragma unroll
-    for (int k = 0; k < OD; ++k) s_obs[threadIdx.x * OD + k] = o[k];
-    reward[e] = r;
-    done[e] = d;
-    success[e] = su;
+    for (int k = 0; k < OD; ++k) st[lane * OD + k] = o[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < OD; ++k) {
+      const int i = k * 32 + lane;
+      if (i < cnt * OD) obs[(size_t)wbase * OD + i] = st[i];
+    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < cnt * OD; i += LANE_BLOCK) obs[(size_t)base * OD + i] = s_obs[i];
+  notify_host(H);
 }
 
 template <int TASK>

@@ -44,6 +44,8 @@ class ArmSimHandle:
 
     def close(self):
         if getattr(self, "h", None):
+            self._hb = None              # the views die with the pinned block
+            self._pinned_call = None
             L.lib().armsim_destroy(self.h)
             self.h = None
 
@@ -76,8 +78,46 @@ class ArmSimHandle:
         return int(L.lib().armsim_launch_count(self.h))
 
     # ---- host-buffer path (numpy in / numpy out; H2D + launch + D2H inside the call)
+    def host_buffers(self):
+        """numpy views (action [n,3], obs [n,obs_dim], reward [n], done [n], success [n]) of the handle's pinned,
+        device-mapped I/O block (armsim_host_buffers).  step_host(action_view, out=the four output views) is the
+        copy-free form of the call: write the actions into `action`, call, read the results in place."""
+        if getattr(self, "_hb", None) is None:
+            ptr = [C.c_void_p() for _ in range(5)]
+            L.check(L.lib().armsim_host_buffers(self.h, *[C.byref(p) for p in ptr]))
+            n = self.n
+
+            def view(p, ctype, dtype, shape):
+                cnt = int(np.prod(shape))
+                return np.frombuffer((ctype * cnt).from_address(p.value), dtype=dtype).reshape(shape)
+            self._hb = (view(ptr[0], C.c_float, np.float32, (n, self.act_dim)),
+                        view(ptr[1], C.c_float, np.float32, (n, self.obs_dim)),
+                        view(ptr[2], C.c_float, np.float32, (n,)),
+                        view(ptr[3], C.c_uint8, np.uint8, (n,)),
+                        view(ptr[4], C.c_uint8, np.uint8, (n,)))
+        return self._hb
+
+    def step_pinned(self):
+        """armsim_step_host on the handle's own pinned block with every argument pre-bound: the leanest host-side call
+        (no per-call ctypes conversions).  Actions are read from host_buffers()[0]; results land in host_buffers()[1:]."""
+        call = getattr(self, "_pinned_call", None)
+        if call is None:
+            hb = self.host_buffers()
+            fn = L.lib().armsim_step_host
+            args = (self.h,) + tuple(C.c_void_p(b.ctypes.data) for b in hb)
+            chk = L.check
+
+            def call():
+                rc = fn(*args)
+                if rc:
+                    chk(rc)
+            self._pinned_call = call
+        call()
+        return self._hb[1:]
+
     def step_host(self, action, out=None):
-        a = np.ascontiguousarray(action, np.float32)
+        a = action if (isinstance(action, np.ndarray) and action.dtype == np.float32 and action.flags.c_contiguous) \
+            else np.ascontiguousarray(action, np.float32)
         if a.shape != (self.n, self.act_dim):
             raise ValueError("action must be [%d, %d], got %s" % (self.n, self.act_dim, a.shape))
         if out is None:

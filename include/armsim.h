@@ -132,11 +132,19 @@ int armsim_reset(ArmSim* sim, const uint8_t* mask_dev, float* obs_dev, void* str
 int armsim_step(ArmSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                 uint8_t* success_dev, void* stream);
 
-/* Same step through HOST buffers (what a host-side Env.step sees): pinned staging, H2D of the actions, the
- * fused launch, D2H of obs/reward/done/success, stream synchronise.  Used for the end-to-end measurement. */
+/* Same step through HOST buffers (what a host-side Env.step sees): the actions cross to the device, the fused
+ * launch runs, obs/reward/done/success cross back, and the call returns when they are in the caller's buffers.
+ * Arbitrary host pointers are staged through the handle's pinned block; see armsim_host_buffers for the copy-free
+ * form.  Used for the end-to-end measurement. */
 int armsim_step_host(ArmSim* sim, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host,
                      uint8_t* success_host);
 int armsim_reset_host(ArmSim* sim, const uint8_t* mask_host, float* obs_host);
+
+/* The handle's own pinned (page-locked, device-mapped) I/O block: action f32 [n, act_dim], obs f32 [n, obs_dim],
+ * reward f32 [n], done u8 [n], success u8 [n].  Passing exactly these pointers to armsim_step_host makes the call
+ * copy-free on the host: for n_envs <= 65536 the kernel reads the actions from and writes the results to this block
+ * over PCIe itself and rings a doorbell in it (no DMA launches, no stream synchronise).  Any pointer may be NULL. */
+int armsim_host_buffers(ArmSim* sim, float** action, float** obs, float** reward, uint8_t** done, uint8_t** success);
 
 /* Inject / read back per-env state (parity tests inject q, goal, cube pose; SURVEY 5 "seeding facts").
  * `bytes` must equal n_envs * width * 4.  Synchronous. */

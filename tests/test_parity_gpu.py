@@ -364,6 +364,63 @@ def test_device_path_equals_host_path(pkg, torch_cuda):
     h.close(); e.close()
 
 
+def test_pinned_host_buffers_are_copy_free_and_equal(pkg, torch_cuda):
+    """armsim_host_buffers: stepping in the handle's own pinned block (zero-copy + doorbell) gives the same bits as
+    the staged call with ordinary numpy buffers, at a ragged n and at n = 1 (the drop-in Env shims' size)"""
+    for n in (1, 333, 4096):
+        rng = np.random.default_rng(n)
+        h1 = pkg.ArmSimHandle("push", n_envs=n, seed=5)
+        h2 = pkg.ArmSimHandle("push", n_envs=n, seed=5)
+        act, obs, rew, done, succ = h1.host_buffers()
+        assert act.shape == (n, 3) and obs.shape == (n, 9)
+        for _ in range(6):
+            a = rng.uniform(-0.4, 0.4, (n, 3)).astype(np.float32)
+            act[:] = a
+            if _ % 2:
+                o1, r1, d1, s1 = h1.step_host(act, out=(obs, rew, done, succ))
+            else:
+                o1, r1, d1, s1 = h1.step_pinned()
+            assert o1 is obs and r1 is rew
+            o2, r2, d2, s2 = h2.step_host(a)
+            assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and np.array_equal(d1, d2) and np.array_equal(s1, s2)
+        h1.close(); h2.close()
+
+
+def test_host_path_large_batch_uses_dma_copies(pkg, torch_cuda):
+    """n > 65536 takes the cudaMemcpyAsync route of armsim_step_host; same results as the device-pointer path"""
+    torch = torch_cuda
+    n = 70001
+    a = np.random.default_rng(2).uniform(-0.7, 0.7, (n, 3)).astype(np.float32)
+    h = pkg.ArmSimHandle("reach", n_envs=n, seed=9)
+    e = pkg.BatchedArmEnv("reach", n_envs=n, seed=9, device="cuda:0")
+    for _ in range(3):
+        oh, rh, dh, sh = h.step_host(a)
+        od, rd, dd, sd = e.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(oh, od.cpu().numpy()) and np.array_equal(rh, rd.cpu().numpy())
+        assert np.array_equal(dh, dd.cpu().numpy())
+    h.close(); e.close()
+
+
+def test_orientation_error_near_half_turn(pkg, oracle, torch_cuda):
+    """IK target orientation ~180 deg from the start pose: the matrix form of the rotation error hands over to the
+    quaternion form (sin(theta) -> 0); one teacher-forced step must still match the oracle"""
+    L, O = pkg._lib, oracle
+    n = 256
+    # start pose R ~ diag(-1, 1, -1) (SURVEY App. A); euler (0, -pi, pi) is ~a half turn away from it about x
+    for rpy in ((0.0, -np.pi, np.pi - 0.05), (0.03, -np.pi + 0.02, np.pi), (0.0, 0.0, 0.0)):
+        env, ora = _pair(pkg, oracle, "reach", n, seed=11, target_rpy=rpy)
+        rng = np.random.default_rng(4)
+        a = rng.uniform(-0.7, 0.7, (n, 3)).astype(np.float32)
+        _sync_state(env, ora, L, O, [O.F_GOAL, O.F_STEP, O.F_Q])
+        og, _, _, _ = env.step_host(a)
+        oo, _, _, _ = ora.step(a)
+        same = env.get_state(L.F_IK_ITERS) == ora.get_state(O.F_IK_ITERS)
+        assert same.mean() > 0.9, same.mean()
+        assert np.abs(env.get_state(L.F_Q) - ora.get_state(O.F_Q))[same].max() <= 5e-4
+        assert np.abs(og[:, :3] - oo[:, :3])[same].max() <= 2e-5
+        env.close(); ora.close()
+
+
 def test_auto_reset_full_size(pkg, torch_cuda):
     """BASELINE config: N = 4096, > 1 episode with in-kernel auto-reset; size-independent properties"""
     torch = torch_cuda
