@@ -46,6 +46,7 @@ class ArmsimConfig(C.Structure):
                 ("target_rpy", C.c_double * 3), ("init_q", C.c_double * NJ),
                 ("ik_damping", C.c_double), ("ik_max_iters", C.c_int32), ("ik_residual", C.c_double),
                 ("clamp_joint_limits", C.c_int32), ("reserved", C.c_int32 * 7),
+                ("sim_dt", C.c_double), ("gravity", C.c_double * 3),
                 ("custom_chain", C.POINTER(ArmsimChain))]
 
 
@@ -88,8 +89,8 @@ def lib():
     L.armsim_launch_count.argtypes = [vp]
     L.armsim_launch_count.restype = C.c_int64
     L.armsim_fk_host.argtypes = [vp, vp, i32, vp, vp]
-    if L.armsim_abi_version() != 1:
-        raise ArmsimError("libarmsim ABI version %d != 1" % L.armsim_abi_version())
+    if L.armsim_abi_version() != 2:
+        raise ArmsimError("libarmsim ABI version %d != 2" % L.armsim_abi_version())
     _lib = L
     return L
 

@@ -36,6 +36,7 @@ struct ArmSim {
   int n = 0, obs_dim = 0, act_dim = 3, mapping = ARMSIM_MAP_LANE;
   ChainParams chain;
   TaskParams task;
+  DynParams dyn;
   StatePtrs S{};
   void* state_block = nullptr;   // one allocation holding every SoA field
   // *_host path: one pinned block + one device block, outputs contiguous so the D2H is a single copy
@@ -92,6 +93,29 @@ static void fill_chain(const Model& m, ChainParams& c) {
     c.lower[j] = (float)m.lower[j];
     c.upper[j] = (float)m.upper[j];
   }
+}
+
+// torque mode: spatial inertia of each link about its frame origin, limits, gravity as a base acceleration
+template <class Model>
+static void fill_dyn(const Model& m, const ArmsimConfig& cfg, DynParams& d) {
+  memset(&d, 0, sizeof(d));
+  for (int j = 0; j < NJ; ++j) {
+    const double mass = m.mass[j], *c = m.com[j], *I = m.inertia[j];
+    const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    const double full[6] = {I[0] + mass * (cc - c[0] * c[0]), I[1] - mass * c[0] * c[1], I[2] - mass * c[0] * c[2],
+                            I[3] + mass * (cc - c[1] * c[1]), I[4] - mass * c[1] * c[2], I[5] + mass * (cc - c[2] * c[2])};
+    for (int k = 0; k < 6; ++k) d.Ibar[j][k] = (float)full[k];
+    for (int k = 0; k < 3; ++k) d.h[j][k] = (float)(mass * c[k]);
+    d.mass[j] = (float)mass;
+    d.effort[j] = (float)m.effort[j];
+    d.maxvel[j] = (float)m.velocity[j];
+    d.damping[j] = (float)m.damping[j];
+  }
+  double Rb[9];
+  rpy_to_mat(m.base_rpy, Rb);
+  for (int i = 0; i < 3; ++i)   // Rb^T (-g)
+    d.abase[i] = (float)(-(Rb[i] * cfg.gravity[0] + Rb[3 + i] * cfg.gravity[1] + Rb[6 + i] * cfg.gravity[2]));
+  d.dt = (float)cfg.sim_dt;
 }
 
 static void quat_from_euler(const double rpy[3], float q[4]) {
@@ -182,9 +206,34 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
     step_lane_kernel<TASK, ROBOT><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su, H);     \
     break;
 
+#define ARMSIM_TORQUE_CASE(TASK, ROBOT)                                                                                \
+  case (TASK) * 4 + (ROBOT):                                                                                           \
+    step_torque_kernel<TASK, ROBOT><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->dyn, s->S, a, o, r, d, su, H);  \
+    break;
+
 static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st,
                        const HostNotify H = HostNotify{nullptr, nullptr, 0u}) {
   const int grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
+  if (s->cfg.mode == ARMSIM_MODE_TORQUE) {
+    switch (s->cfg.task * 4 + s->cfg.robot) {
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_KUKA_IIWA)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_DIANA_S1)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_CUSTOM)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_PUSH, ARMSIM_ROBOT_KUKA_IIWA)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_PUSH, ARMSIM_ROBOT_DIANA_S1)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_PUSH, ARMSIM_ROBOT_CUSTOM)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_PICK, ARMSIM_ROBOT_KUKA_IIWA)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_PICK, ARMSIM_ROBOT_DIANA_S1)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_PICK, ARMSIM_ROBOT_CUSTOM)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_KUKA_IIWA)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_DIANA_S1)
+      ARMSIM_TORQUE_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_CUSTOM)
+      default: return fail(ARMSIM_E_INVALID, "bad task / robot");
+    }
+    s->launches += 1;
+    CU(cudaGetLastError());
+    return ARMSIM_OK;
+  }
   switch (s->cfg.task * 4 + s->cfg.robot) {
     ARMSIM_STEP_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_KUKA_IIWA)
     ARMSIM_STEP_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_DIANA_S1)
@@ -212,7 +261,8 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
     return fail(ARMSIM_E_INVALID, "armsim_create: struct_size %d != %zu (ABI mismatch)", cfg->struct_size, sizeof(ArmsimConfig));
   if (cfg->n_envs <= 0) return fail(ARMSIM_E_INVALID, "armsim_create: n_envs must be > 0");
   if (cfg->task < 0 || cfg->task > ARMSIM_TASK_KUKA_REACH) return fail(ARMSIM_E_INVALID, "armsim_create: bad task %d", cfg->task);
-  if (cfg->mode != ARMSIM_MODE_IK_TELEPORT) return fail(ARMSIM_E_INVALID, "armsim_create: mode %d not available in this build", cfg->mode);
+  if (cfg->mode != ARMSIM_MODE_IK_TELEPORT && cfg->mode != ARMSIM_MODE_TORQUE) return fail(ARMSIM_E_INVALID, "armsim_create: bad mode %d", cfg->mode);
+  if (cfg->mode == ARMSIM_MODE_TORQUE && !(cfg->sim_dt > 0.0)) return fail(ARMSIM_E_INVALID, "armsim_create: torque mode needs sim_dt > 0");
   if (cfg->ik_max_iters < 0 || cfg->max_steps < 0) return fail(ARMSIM_E_INVALID, "armsim_create: negative iteration / step limit");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -228,9 +278,9 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   s->cfg.custom_chain = nullptr;
   s->n = cfg->n_envs;
   double ee0[3], R0[9];
-  if (cfg->robot == ARMSIM_ROBOT_KUKA_IIWA) { fill_chain(ARMSIM_MODEL_KUKA_IIWA, s->chain); host_fk(ARMSIM_MODEL_KUKA_IIWA, cfg->init_q, ee0, R0); }
-  else if (cfg->robot == ARMSIM_ROBOT_DIANA_S1) { fill_chain(ARMSIM_MODEL_DIANA_S1, s->chain); host_fk(ARMSIM_MODEL_DIANA_S1, cfg->init_q, ee0, R0); }
-  else if (cfg->robot == ARMSIM_ROBOT_CUSTOM && cfg->custom_chain) { fill_chain(*cfg->custom_chain, s->chain); host_fk(*cfg->custom_chain, cfg->init_q, ee0, R0); }
+  if (cfg->robot == ARMSIM_ROBOT_KUKA_IIWA) { fill_chain(ARMSIM_MODEL_KUKA_IIWA, s->chain); fill_dyn(ARMSIM_MODEL_KUKA_IIWA, *cfg, s->dyn); host_fk(ARMSIM_MODEL_KUKA_IIWA, cfg->init_q, ee0, R0); }
+  else if (cfg->robot == ARMSIM_ROBOT_DIANA_S1) { fill_chain(ARMSIM_MODEL_DIANA_S1, s->chain); fill_dyn(ARMSIM_MODEL_DIANA_S1, *cfg, s->dyn); host_fk(ARMSIM_MODEL_DIANA_S1, cfg->init_q, ee0, R0); }
+  else if (cfg->robot == ARMSIM_ROBOT_CUSTOM && cfg->custom_chain) { fill_chain(*cfg->custom_chain, s->chain); fill_dyn(*cfg->custom_chain, *cfg, s->dyn); host_fk(*cfg->custom_chain, cfg->init_q, ee0, R0); }
   else { delete s; return fail(ARMSIM_E_INVALID, "armsim_create: bad robot %d (custom needs custom_chain)", cfg->robot); }
 
   TaskParams& T = s->task;
@@ -238,7 +288,9 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   T.task = cfg->task; T.n = s->n; T.max_steps = cfg->max_steps; T.auto_reset = cfg->auto_reset ? 1 : 0;
   T.ik_max_iters = cfg->ik_max_iters; T.napply = cfg->task == ARMSIM_TASK_PICK ? 6 : NJ;
   T.clamp = cfg->clamp_joint_limits ? 1 : 0;
-  T.obs_dim = s->obs_dim = cfg->task == ARMSIM_TASK_REACH ? 6 : (cfg->task == ARMSIM_TASK_KUKA_REACH ? 3 : 9);
+  T.torque_mode = cfg->mode == ARMSIM_MODE_TORQUE ? 1 : 0;
+  s->act_dim = T.torque_mode ? ARMSIM_TORQUE_DIM : ARMSIM_ACT_DIM;
+  T.obs_dim = s->obs_dim = (cfg->task == ARMSIM_TASK_REACH ? 6 : (cfg->task == ARMSIM_TASK_KUKA_REACH ? 3 : 9)) + (T.torque_mode ? 2 * NJ : 0);
   T.dv = (float)cfg->dv; T.reach_dis = (float)cfg->reach_dis; T.ik_damping = (float)cfg->ik_damping; T.ik_residual = (float)cfg->ik_residual;
   for (int i = 0; i < 3; ++i) {
     T.ws_lo[i] = (float)cfg->ws_lo[i]; T.ws_hi[i] = (float)cfg->ws_hi[i];

@@ -20,7 +20,7 @@ struct ChainParams {
 };
 
 struct TaskParams {
-  int task, n, max_steps, auto_reset, ik_max_iters, napply, clamp, obs_dim;
+  int task, n, max_steps, auto_reset, ik_max_iters, napply, clamp, obs_dim, torque_mode;
   float dv, reach_dis, ik_damping, ik_residual;
   float ws_lo[3], ws_hi[3];
   float goal_lo[3], goal_span[3];

@@ -7,6 +7,7 @@
 // done / success -> optional in-kernel auto-reset (Philox) -> obs.
 #pragma once
 #include "armsim_device.cuh"
+#include "aba_device.cuh"
 #include "cube_model.cuh"
 
 constexpr int LANE_BLOCK = 128;
@@ -63,6 +64,10 @@ __device__ __forceinline__ void reset_env(const ChainParams& C, const TaskParams
   cube::State cb;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) { q[j] = T.init_q[j]; S.q[j * n + e] = q[j]; }
+  if (T.torque_mode) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) S.qd[j * n + e] = 0.f;
+  }
   if constexpr (!TaskTraits<TASK>::HAS_CUBE) {
     reset_uniforms(T, gid, ep, 0u, u);
 #pragma unroll
@@ -112,7 +117,7 @@ __device__ __forceinline__ void reset_env(const ChainParams& C, const TaskParams
 // Per-env state of one step, held in registers between the load and the store phase.
 template <int TASK>
 struct EnvRegs {
-  float q[NJ], goal[3];
+  float q[NJ], qd[NJ], goal[3];
   int stepc;
   uint8_t latched;     // done flag latched by a previous step (auto_reset = 0)
   cube::State cb;
@@ -136,26 +141,18 @@ __device__ __forceinline__ void load_env(const TaskParams& T, const StatePtrs& S
   }
 }
 
-// Env.step() for one env on pre-loaded registers.  Returns through o / r / d / su; `live` = false lanes (padding of
-// the last warp) compute on a clone of the last env and store nothing.
-template <int TASK, int ROBOT>
-__device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams& T, const StatePtrs& S, int e, bool live,
-                                         EnvRegs<TASK>& E, const float (&a)[3], float (&o)[TaskTraits<TASK>::OBS],
-                                         float& r, uint8_t& d, uint8_t& su) {
+// Everything of Env.step() after the arm has moved: cube / gripper contact step(s), reward, done, success, state
+// write-back, auto-reset, observation.  p, R = EE link frame of the state in E.q.  Returns true when the env was
+// re-initialised in place (auto-reset), i.e. the stored q is init_q again.
+template <int TASK>
+__device__ __forceinline__ bool task_epilogue(const ChainParams& C, const TaskParams& T, const StatePtrs& S, int e, bool live,
+                                              EnvRegs<TASK>& E, const float (&p)[3], const float (&R)[9], int its,
+                                              float (&o)[TaskTraits<TASK>::OBS], float& r, uint8_t& d, uint8_t& su) {
   const int n = T.n;
   float (&q)[NJ] = E.q;
   float (&goal)[3] = E.goal;
   cube::State& cb = E.cb;
   int stepc = E.stepc;
-
-  float p[3], R[9];
-  const bool frozen = E.latched != 0;               // finished env waiting for reset: report its frozen state
-  const int its = servo_core<ROBOT, TASK != ARMSIM_TASK_KUKA_REACH>(C, T, a, frozen, q, p, R);
-  if (frozen) {
-    make_obs<TASK>(p, goal, cb, o);
-    r = 0.f; d = 1; su = 0;
-    return;
-  }
   if (live) {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) S.q[j * n + e] = q[j];           // resetJointState :252-257
@@ -206,14 +203,32 @@ __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams&
   }
   d = term ? 1 : 0;
   su = succ ? 1 : 0;
-  if (!live) { make_obs<TASK>(p, goal, cb, o); return; }
+  if (!live) { make_obs<TASK>(p, goal, cb, o); return false; }
   S.step[e] = stepc;
   if (term && T.auto_reset) {
     reset_env<TASK>(C, T, S, e, o);
-  } else {
-    if (term) S.done[e] = 1;
-    make_obs<TASK>(p, goal, cb, o);
+    return true;
   }
+  if (term) S.done[e] = 1;
+  make_obs<TASK>(p, goal, cb, o);
+  return false;
+}
+
+// Env.step() for one env on pre-loaded registers (IK-teleport mode, what the reference does).  Returns through
+// o / r / d / su; `live` = false lanes (padding of the last warp) compute on a clone of the last env and store nothing.
+template <int TASK, int ROBOT>
+__device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams& T, const StatePtrs& S, int e, bool live,
+                                         EnvRegs<TASK>& E, const float (&a)[3], float (&o)[TaskTraits<TASK>::OBS],
+                                         float& r, uint8_t& d, uint8_t& su) {
+  float p[3], R[9];
+  const bool frozen = E.latched != 0;               // finished env waiting for reset: report its frozen state
+  const int its = servo_core<ROBOT, TASK != ARMSIM_TASK_KUKA_REACH>(C, T, a, frozen, E.q, p, R);
+  if (frozen) {
+    make_obs<TASK>(p, E.goal, E.cb, o);
+    r = 0.f; d = 1; su = 0;
+    return;
+  }
+  task_epilogue<TASK>(C, T, S, e, live, E, p, R, its, o, r, d, su);
 }
 
 // Completion doorbell of the host-buffer path (armsim_step_host): when `flag` is non-null the kernel's outputs go
@@ -294,6 +309,82 @@ step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ 
   notify_host(H);
 }
 
+// Torque mode: one launch = one dynamics step of the whole batch.  action [n,7] joint torques; obs [n, OBS+14] = the
+// task observation followed by q[7], qd[7].  Same warp-local staging as the IK kernel.
+template <int TASK, int ROBOT>
+__global__ void __launch_bounds__(LANE_BLOCK)
+step_torque_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T,
+                   const __grid_constant__ DynParams Dn, const StatePtrs S, const float* __restrict__ action,
+                   float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
+                   uint8_t* __restrict__ success, const HostNotify H) {
+  constexpr int OB = TaskTraits<TASK>::OBS;
+  constexpr int OD = OB + 2 * NJ;
+  __shared__ float s_io[LANE_BLOCK / 32][32 * OD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wbase = blockIdx.x * LANE_BLOCK + warp * 32;
+  if (wbase < T.n) {
+    const int n = T.n;
+    const int cnt = min(32, n - wbase);
+    const bool live = lane < cnt;
+    const int e = wbase + min(lane, cnt - 1);
+    float* st = s_io[warp];
+
+    float araw[NJ];
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      const int i = k * 32 + lane;
+      araw[k] = i < cnt * NJ ? __ldg(action + (size_t)wbase * NJ + i) : 0.f;
+    }
+    EnvRegs<TASK> E;
+    load_env<TASK>(T, S, e, E);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) E.qd[j] = S.qd[j * n + e];
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) st[k * 32 + lane] = araw[k];
+    __syncwarp();
+    float cmd[NJ];
+    const int al = min(lane, cnt - 1) * NJ;
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) cmd[k] = st[al + k];
+    __syncwarp();
+
+    float o[OB], r = 0.f, p[3], R[9], P[NJ][3], Z[NJ][3];
+    uint8_t d = 1, su = 0;
+    bool was_reset = false;
+    const bool frozen = E.latched != 0;
+    if (!frozen) aba::torque_step(C, Dn, cmd, E.q, E.qd);
+    RobotFK<ROBOT>::template run<false>(C, E.q, p, R, P, Z);
+    if (frozen) {
+      make_obs<TASK>(p, E.goal, E.cb, o);
+    } else {
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) S.qd[j * n + e] = E.qd[j];
+      }
+      was_reset = task_epilogue<TASK>(C, T, S, e, live, E, p, R, 0, o, r, d, su);
+    }
+    if (live) {
+      reward[e] = r;
+      done[e] = d;
+      success[e] = su;
+    }
+#pragma unroll
+    for (int k = 0; k < OB; ++k) st[lane * OD + k] = o[k];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      st[lane * OD + OB + j] = was_reset ? T.init_q[j] : E.q[j];
+      st[lane * OD + OB + NJ + j] = was_reset ? 0.f : E.qd[j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < OD; ++k) {
+      const int i = k * 32 + lane;
+      if (i < cnt * OD) obs[(size_t)wbase * OD + i] = st[i];
+    }
+  }
+  notify_host(H);
+}
+
 template <int TASK>
 __global__ void __launch_bounds__(LANE_BLOCK)
 reset_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T, const StatePtrs S,
@@ -305,8 +396,13 @@ reset_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__
   float o[OD];
   reset_env<TASK>(C, T, S, e, o);
   if (obs) {
+    const int stride = T.obs_dim;     // OD, or OD + 14 in torque mode
 #pragma unroll
-    for (int k = 0; k < OD; ++k) obs[(size_t)e * OD + k] = o[k];
+    for (int k = 0; k < OD; ++k) obs[(size_t)e * stride + k] = o[k];
+    if (T.torque_mode) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { obs[(size_t)e * stride + OD + j] = T.init_q[j]; obs[(size_t)e * stride + OD + NJ + j] = 0.f; }
+    }
   }
 }
 

@@ -12,15 +12,19 @@ from .. import _lib as L
 
 _TASKS = {"reach": L.TASK_REACH, "push": L.TASK_PUSH, "pick": L.TASK_PICK, "kuka_reach": L.TASK_KUKA_REACH}
 _ROBOTS = {"kuka_iiwa": L.ROBOT_KUKA_IIWA, "diana_s1": L.ROBOT_DIANA_S1}
+_MODES = {"ik_teleport": L.MODE_IK_TELEPORT, "torque": L.MODE_TORQUE}
 
 
 class ArmSimHandle:
     """Thin RAII wrapper of an ArmSim* (create / destroy / state io); no torch needed."""
 
     def __init__(self, task="reach", n_envs=1, device=0, robot="kuka_iiwa", seed=0, env_id_offset=0, auto_reset=False,
-                 chain=None, **overrides):
+                 chain=None, mode="ik_teleport", **overrides):
+        """mode = "ik_teleport": the reference's step (action [n,3] EE servo).  mode = "torque": joint torques
+        [n,7] through articulated-body forward dynamics (obs = task obs + q[7] + qd[7])."""
         task_id = _TASKS[task] if isinstance(task, str) else int(task)
         cfg = L.default_config(task_id, **overrides)
+        cfg.mode = _MODES[mode] if isinstance(mode, str) else int(mode)
         cfg.n_envs = int(n_envs)
         cfg.device = int(device)
         cfg.seed = int(seed)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ARMSIM_ABI_VERSION 1
+#define ARMSIM_ABI_VERSION 2
 #define ARMSIM_NJ 7            /* arm joints (Kuka iiwa, DianaS1) */
 #define ARMSIM_ACT_DIM 3       /* Cartesian EE servo action, reference envs' action_space */
 #define ARMSIM_TORQUE_DIM 7    /* torque mode action */
@@ -48,7 +48,9 @@ enum {
 enum { ARMSIM_ROBOT_KUKA_IIWA = 0, ARMSIM_ROBOT_DIANA_S1 = 1, ARMSIM_ROBOT_CUSTOM = 2 };
 enum {
   ARMSIM_MODE_IK_TELEPORT = 0, /* what the reference does: EE target -> DLS IK -> teleport joints */
-  ARMSIM_MODE_TORQUE = 1       /* north-star addition: joint torques -> ABA forward dynamics -> integrate      */
+  ARMSIM_MODE_TORQUE = 1       /* north-star addition: joint torques [n,7] -> effort clip + joint damping -> ABA forward
+                                  dynamics -> semi-implicit Euler (sim_dt) -> velocity clip -> joint-limit clamp -> the
+                                  task's reward.  obs = task obs followed by q[7], qd[7] (obs_dim + 14)              */
 };
 enum {
   ARMSIM_MAP_AUTO = 0,         /* pick by n_envs */
@@ -85,6 +87,8 @@ typedef struct ArmsimConfig {
   double ik_residual;          /* Bullet default 1e-4 */
   int32_t clamp_joint_limits;  /* 0 = reference behaviour (no clamp in IK mode); torque mode always clamps */
   int32_t reserved[7];
+  double sim_dt;               /* torque mode: integration step, Bullet default 1/240 s (p.stepSimulation) */
+  double gravity[3];           /* torque mode: world gravity, (0,0,-10) (rl_reach_env.py:142 p.setGravity) */
   const ArmsimChain* custom_chain; /* only for ARMSIM_ROBOT_CUSTOM */
 } ArmsimConfig;
 

@@ -57,6 +57,8 @@ static inline int armsim_fill_default_config(int32_t task, ArmsimConfig* c) {
   c->ik_max_iters = 20;                       /* Bullet default maxNumIterations */
   c->ik_residual = 1e-4;                     /* Bullet default residualThreshold */
   c->clamp_joint_limits = 0;
+  c->sim_dt = 1.0 / 240.0;                   /* Bullet default fixedTimeStep used by p.stepSimulation() */
+  c->gravity[0] = 0.0; c->gravity[1] = 0.0; c->gravity[2] = -10.0;   /* rl_reach_env.py:142 */
   c->custom_chain = NULL;
   return ARMSIM_OK;
 }

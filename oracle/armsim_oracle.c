@@ -19,6 +19,7 @@
 #include "armsim_defaults.h"
 #include "armsim_robot_models.h"
 #include "cube_model.h"
+#include "aba_model.h"
 
 #define NJ ARMSIM_NJ
 
@@ -56,6 +57,8 @@ typedef struct OrcChain {
   double Rb[9], tb[3];          /* base */
   double Rf[NJ][9], t[NJ][3];   /* fixed joint-origin transform per joint */
   double lower[NJ], upper[NJ];
+  double effort[NJ], velocity[NJ], damping[NJ];   /* torque mode */
+  AbaChain dyn;
 } OrcChain;
 
 static void rpy_to_mat(const double rpy[3], double R[9]) {
@@ -76,23 +79,43 @@ static void mat_mul(const double A[9], const double B[9], double C[9]) {
 static void chain_from_model(const ArmsimRobotModel* m, OrcChain* c) {
   rpy_to_mat(m->base_rpy, c->Rb);
   memcpy(c->tb, m->base_xyz, sizeof(c->tb));
+  memcpy(c->dyn.Rb, c->Rb, sizeof(c->Rb));
   for (int j = 0; j < NJ; ++j) {
     rpy_to_mat(m->rpy[j], c->Rf[j]);
     memcpy(c->t[j], m->xyz[j], sizeof(c->t[j]));
     c->lower[j] = m->lower[j];
     c->upper[j] = m->upper[j];
+    c->effort[j] = m->effort[j];
+    c->velocity[j] = m->velocity[j];
+    c->damping[j] = m->damping[j];
+    memcpy(c->dyn.Rf[j], c->Rf[j], sizeof(c->Rf[j]));
+    memcpy(c->dyn.t[j], c->t[j], sizeof(c->t[j]));
+    c->dyn.mass[j] = m->mass[j];
+    memcpy(c->dyn.com[j], m->com[j], sizeof(c->dyn.com[j]));
+    memcpy(c->dyn.Ic[j], m->inertia[j], sizeof(c->dyn.Ic[j]));
   }
+  c->dyn.gravity[0] = 0.0; c->dyn.gravity[1] = 0.0; c->dyn.gravity[2] = -10.0;
 }
 
 static void chain_from_custom(const ArmsimChain* m, OrcChain* c) {
   rpy_to_mat(m->base_rpy, c->Rb);
   memcpy(c->tb, m->base_xyz, sizeof(c->tb));
+  memcpy(c->dyn.Rb, c->Rb, sizeof(c->Rb));
   for (int j = 0; j < NJ; ++j) {
     rpy_to_mat(m->rpy[j], c->Rf[j]);
     memcpy(c->t[j], m->xyz[j], sizeof(c->t[j]));
     c->lower[j] = m->lower[j];
     c->upper[j] = m->upper[j];
+    c->effort[j] = m->effort[j];
+    c->velocity[j] = m->velocity[j];
+    c->damping[j] = m->damping[j];
+    memcpy(c->dyn.Rf[j], c->Rf[j], sizeof(c->Rf[j]));
+    memcpy(c->dyn.t[j], c->t[j], sizeof(c->t[j]));
+    c->dyn.mass[j] = m->mass[j];
+    memcpy(c->dyn.com[j], m->com[j], sizeof(c->dyn.com[j]));
+    memcpy(c->dyn.Ic[j], m->inertia[j], sizeof(c->dyn.Ic[j]));
   }
+  c->dyn.gravity[0] = 0.0; c->dyn.gravity[1] = 0.0; c->dyn.gravity[2] = -10.0;
 }
 
 static int chain_builtin(int32_t robot, OrcChain* c) {
@@ -284,6 +307,28 @@ int orc_ik(int32_t robot, const double q_in[7], const double target_pos[3], cons
   return chain_ik(&c, q_in, target_pos, target_quat_xyzw, damping, max_iters, residual, q_out, final_diff);
 }
 
+/* torque-mode dynamics of a built-in chain (aba_model.h); gravity (0,0,-10) */
+int orc_aba(int32_t robot, const double q[7], const double qd[7], const double tau[7], double qdd[7]) {
+  OrcChain c;
+  if (chain_builtin(robot, &c)) return -1;
+  aba_forward_dynamics(&c.dyn, q, qd, tau, qdd);
+  return 0;
+}
+
+int orc_rnea(int32_t robot, const double q[7], const double qd[7], const double qdd[7], int with_gravity, double tau[7]) {
+  OrcChain c;
+  if (chain_builtin(robot, &c)) return -1;
+  rnea_inverse_dynamics(&c.dyn, q, qd, qdd, with_gravity, tau);
+  return 0;
+}
+
+int orc_dense_fd(int32_t robot, const double q[7], const double qd[7], const double tau[7], double qdd[7], double M[49]) {
+  OrcChain c;
+  if (chain_builtin(robot, &c)) return -1;
+  dense_forward_dynamics(&c.dyn, q, qd, tau, qdd, M);
+  return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------ sim */
 struct OrcSim {
   ArmsimConfig cfg;
@@ -291,6 +336,7 @@ struct OrcSim {
   double tquat[4];
   int n;
   double (*q)[NJ];
+  double (*qd)[NJ];     /* torque mode */
   float (*goal)[3];     /* reach goal / push,pick target -- held as f32 like `object_state.astype(np.float32)` */
   int32_t* step;
   int32_t* episode;
@@ -301,13 +347,16 @@ struct OrcSim {
   double* grip;
 };
 
-int32_t orc_obs_dim(const OrcSim* s) {
+static int32_t base_obs_dim(const OrcSim* s) {
   switch (s->cfg.task) {
     case ARMSIM_TASK_REACH: return 6;
     case ARMSIM_TASK_KUKA_REACH: return 3;
     default: return 9;
   }
 }
+
+int32_t orc_obs_dim(const OrcSim* s) { return base_obs_dim(s) + (s->cfg.mode == ARMSIM_MODE_TORQUE ? 2 * NJ : 0); }
+int32_t orc_action_dim(const OrcSim* s) { return s->cfg.mode == ARMSIM_MODE_TORQUE ? ARMSIM_TORQUE_DIM : ARMSIM_ACT_DIM; }
 
 OrcSim* orc_create(const ArmsimConfig* cfg) {
   if (!cfg || cfg->struct_size != (int32_t)sizeof(ArmsimConfig) || cfg->n_envs <= 0) return NULL;
@@ -318,8 +367,10 @@ OrcSim* orc_create(const ArmsimConfig* cfg) {
     chain_from_custom(cfg->custom_chain, &s->chain);
   } else if (chain_builtin(cfg->robot, &s->chain)) { free(s); return NULL; }
   orc_quat_from_euler(cfg->target_rpy, s->tquat);
+  memcpy(s->chain.dyn.gravity, cfg->gravity, sizeof(cfg->gravity));
   int n = s->n = cfg->n_envs;
   s->q = calloc(n, sizeof(*s->q));
+  s->qd = calloc(n, sizeof(*s->qd));
   s->goal = calloc(n, sizeof(*s->goal));
   s->step = calloc(n, sizeof(int32_t));
   s->episode = calloc(n, sizeof(int32_t));
@@ -334,7 +385,7 @@ OrcSim* orc_create(const ArmsimConfig* cfg) {
 
 void orc_destroy(OrcSim* s) {
   if (!s) return;
-  free(s->q); free(s->goal); free(s->step); free(s->episode); free(s->ik_iters); free(s->done);
+  free(s->q); free(s->qd); free(s->goal); free(s->step); free(s->episode); free(s->ik_iters); free(s->done);
   free(s->cube); free(s->last_dist); free(s->grip);
   free(s);
 }
@@ -351,6 +402,10 @@ static void write_obs(const OrcSim* s, int e, const double ee[3], float* obs) {
     for (int i = 0; i < 3; ++i) o[3 + i] = (float)s->cube[e].pos[i];
     for (int i = 0; i < 3; ++i) o[6 + i] = s->goal[e][i];
   }
+  if (s->cfg.mode == ARMSIM_MODE_TORQUE) {
+    const int b = base_obs_dim(s);
+    for (int j = 0; j < NJ; ++j) { o[b + j] = (float)s->q[e][j]; o[b + NJ + j] = (float)s->qd[e][j]; }
+  }
 }
 
 /* Env.reset(): rl_reach_env.py:132-217, rl_push_env.py:145-256, rl_pick_env.py:141-256, kuka_reach_env.py:133-212.
@@ -361,7 +416,7 @@ static void reset_env(OrcSim* s, int e, float* obs) {
   const ArmsimConfig* c = &s->cfg;
   const uint64_t gid = c->env_id_offset + (uint64_t)e;
   const uint32_t ep = (uint32_t)s->episode[e];
-  for (int j = 0; j < NJ; ++j) s->q[e][j] = c->init_q[j];   /* resetJointState(i, init_joint_positions[i]) :193-198 */
+  for (int j = 0; j < NJ; ++j) { s->q[e][j] = c->init_q[j]; s->qd[e][j] = 0.0; }  /* resetJointState(i, init_joint_positions[i]) :193-198 */
   s->step[e] = 0;                                           /* :135 */
   s->done[e] = 0;
   s->ik_iters[e] = 0;
@@ -425,6 +480,13 @@ static void step_env(OrcSim* s, int e, const float* action, float* obs, double* 
     reward[e] = 0.0; done[e] = 1; success[e] = 0;
     return;
   }
+  if (c->mode == ARMSIM_MODE_TORQUE) {
+    /* north-star addition: the servo + teleport is replaced by one dynamics step */
+    aba_torque_step(&s->chain.dyn, s->chain.effort, s->chain.velocity, s->chain.damping, s->chain.lower, s->chain.upper,
+                    c->sim_dt, action + (size_t)e * ARMSIM_TORQUE_DIM, s->q[e], s->qd[e]);
+    s->ik_iters[e] = 0;
+    goto after_servo;
+  }
   const float* a = action + (size_t)e * ARMSIM_ACT_DIM;
   double cur[3], Rcur[9];
   chain_fk(&s->chain, s->q[e], cur, Rcur, NULL, NULL);                  /* current_pos = getLinkState(...)[4]  :237 */
@@ -443,6 +505,7 @@ static void step_env(OrcSim* s, int e, const float* action, float* obs, double* 
   for (int j = 0; j < napply; ++j) s->q[e][j] = qn[j];
   if (c->clamp_joint_limits)
     for (int j = 0; j < NJ; ++j) s->q[e][j] = clip_val(s->q[e][j], s->chain.lower[j], s->chain.upper[j]);
+after_servo:;
   /* p.stepSimulation() :258 -- the arm is held by Bullet's default velocity motors: static */
   double ee[3], Ree[9];
   chain_fk(&s->chain, s->q[e], ee, Ree, NULL, NULL);
@@ -527,6 +590,7 @@ static int field_width(int32_t f) {
 static double* field_f64(OrcSim* s, int32_t f, int e) {
   switch (f) {
     case ARMSIM_F_Q: return s->q[e];
+    case ARMSIM_F_QD: return s->qd[e];
     case ARMSIM_F_CUBE_POS: return s->cube[e].pos;
     case ARMSIM_F_CUBE_QUAT: return s->cube[e].quat;
     case ARMSIM_F_CUBE_LINVEL: return s->cube[e].v;

@@ -36,6 +36,11 @@ int orc_jacobian(int32_t robot, const double q[7], double J[42]);
 int orc_ik(int32_t robot, const double q_in[7], const double target_pos[3], const double target_quat_xyzw[4],
            double damping, int max_iters, double residual, double q_out[7], double* final_diff);
 void orc_quat_from_euler(const double rpy[3], double quat_xyzw[4]);
+/* torque-mode dynamics (oracle/aba_model.h): articulated-body forward dynamics, recursive Newton-Euler inverse
+ * dynamics, and the dense route qdd = M^-1 (tau - h) built from RNEA (M optional, 7x7 row-major) */
+int orc_aba(int32_t robot, const double q[7], const double qd[7], const double tau[7], double qdd[7]);
+int orc_rnea(int32_t robot, const double q[7], const double qd[7], const double qdd[7], int with_gravity, double tau[7]);
+int orc_dense_fd(int32_t robot, const double q[7], const double qd[7], const double tau[7], double qdd[7], double M[49]);
 
 OrcSim* orc_create(const ArmsimConfig* cfg);
 void orc_destroy(OrcSim* s);
@@ -49,6 +54,7 @@ int orc_set_state(OrcSim* s, int32_t field, const void* src, size_t bytes);
 int orc_get_state(OrcSim* s, int32_t field, void* dst, size_t bytes);
 int orc_get_state_f64(OrcSim* s, int32_t field, double* dst, size_t count);
 int32_t orc_obs_dim(const OrcSim* s);
+int32_t orc_action_dim(const OrcSim* s);
 int orc_default_config(int32_t task, ArmsimConfig* cfg);
 
 #ifdef __cplusplus

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "liboracle.so")
 NJ = 7
 TASK_REACH, TASK_PUSH, TASK_PICK, TASK_KUKA_REACH = 0, 1, 2, 3
 ROBOT_KUKA, ROBOT_DIANA, ROBOT_CUSTOM = 0, 1, 2
+MODE_IK_TELEPORT, MODE_TORQUE = 0, 1
 (F_Q, F_QD, F_GOAL, F_STEP, F_EPISODE, F_CUBE_POS, F_CUBE_QUAT, F_CUBE_LINVEL, F_CUBE_ANGVEL, F_LAST_DIST, F_GRIP,
  F_IK_ITERS) = range(12)
 FIELD_WIDTH = {F_Q: 7, F_QD: 7, F_GOAL: 3, F_STEP: 1, F_EPISODE: 1, F_CUBE_POS: 3, F_CUBE_QUAT: 4, F_CUBE_LINVEL: 3,
@@ -44,6 +45,7 @@ class ArmsimConfig(C.Structure):
                 ("target_rpy", C.c_double * 3), ("init_q", C.c_double * NJ),
                 ("ik_damping", C.c_double), ("ik_max_iters", C.c_int32), ("ik_residual", C.c_double),
                 ("clamp_joint_limits", C.c_int32), ("reserved", C.c_int32 * 7),
+                ("sim_dt", C.c_double), ("gravity", C.c_double * 3),
                 ("custom_chain", C.POINTER(ArmsimChain))]
 
 
@@ -85,6 +87,11 @@ def lib():
         L.orc_get_state_f64.argtypes = [C.c_void_p, C.c_int32, dp, C.c_size_t]
         L.orc_obs_dim.argtypes = [C.c_void_p]
         L.orc_obs_dim.restype = C.c_int32
+        L.orc_action_dim.argtypes = [C.c_void_p]
+        L.orc_action_dim.restype = C.c_int32
+        L.orc_aba.argtypes = [C.c_int32, dp, dp, dp, dp]
+        L.orc_rnea.argtypes = [C.c_int32, dp, dp, dp, C.c_int, dp]
+        L.orc_dense_fd.argtypes = [C.c_int32, dp, dp, dp, dp, dp]
         if hasattr(L, "orc_default_config"):
             L.orc_default_config.argtypes = [C.c_int32, C.POINTER(ArmsimConfig)]
         _lib = L
@@ -141,6 +148,30 @@ def ik(q, target_pos, target_quat, damping=1e-5, max_iters=20, residual=1e-4, ro
     return out, its, float(diff[0])
 
 
+def aba(q, qd, tau, robot=ROBOT_KUKA):
+    """articulated-body forward dynamics (gravity (0,0,-10)): qdd"""
+    q, qd, tau = (np.ascontiguousarray(x, dtype=np.float64) for x in (q, qd, tau))
+    out = np.zeros(7)
+    assert lib().orc_aba(robot, _dp(q), _dp(qd), _dp(tau), _dp(out)) == 0
+    return out
+
+
+def rnea(q, qd, qdd, robot=ROBOT_KUKA, gravity=True):
+    """recursive Newton-Euler inverse dynamics: tau"""
+    q, qd, qdd = (np.ascontiguousarray(x, dtype=np.float64) for x in (q, qd, qdd))
+    out = np.zeros(7)
+    assert lib().orc_rnea(robot, _dp(q), _dp(qd), _dp(qdd), 1 if gravity else 0, _dp(out)) == 0
+    return out
+
+
+def dense_fd(q, qd, tau, robot=ROBOT_KUKA):
+    """qdd = M^-1 (tau - h) with M, h from RNEA; returns (qdd, M)"""
+    q, qd, tau = (np.ascontiguousarray(x, dtype=np.float64) for x in (q, qd, tau))
+    out, M = np.zeros(7), np.zeros(49)
+    assert lib().orc_dense_fd(robot, _dp(q), _dp(qd), _dp(tau), _dp(out), _dp(M)) == 0
+    return out, M.reshape(7, 7)
+
+
 def philox(ctr, key):
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)
@@ -166,6 +197,7 @@ class OracleSim:
             raise ValueError("orc_create failed (bad config)")
         self.n = cfg.n_envs
         self.obs_dim = lib().orc_obs_dim(self.h)
+        self.act_dim = lib().orc_action_dim(self.h)
         self.obs = np.zeros((self.n, self.obs_dim), np.float32)
         self.reward = np.zeros(self.n, np.float64)
         self.done = np.zeros(self.n, np.uint8)
@@ -185,7 +217,7 @@ class OracleSim:
 
     def step(self, action, lo=0, hi=None):
         a = np.ascontiguousarray(action, np.float32)
-        assert a.shape == (self.n, 3)
+        assert a.shape == (self.n, self.act_dim)
         lib().orc_step_range(self.h, lo, self.n if hi is None else hi, a.ctypes.data, self.obs.ctypes.data,
                              self.reward.ctypes.data, self.done.ctypes.data, self.success.ctypes.data)
         return self.obs.copy(), self.reward.copy(), self.done.copy(), self.success.copy()

@@ -283,3 +283,98 @@ def test_push_cube_moves_when_pushed(oracle):
     c1 = s.get_state_f64(O.F_CUBE_POS)[0]
     assert c1[0] < c0[0] - 0.03, (c0, c1)
     assert abs(c1[2] + 0.005) < 2e-3
+
+
+# --------------------------------------------------------------------------------------------- torque mode (ABA)
+def _numpy_link_frames(robot_name, q):
+    """independent numpy FK: world rotation / origin of every link frame (for the potential energy)"""
+    import json
+    m = json.load(open(os.path.join(os.path.dirname(__file__), "..", "drl-on-robot-arm_b200", "robots", robot_name + ".json")))
+
+    def rpy(r, p, y):
+        cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+        return np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                         [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                         [-sp, cp * sr, cp * cr]])
+    R = rpy(*m["base_rpy"]); p = np.array(m["base_xyz"], float)
+    frames = []
+    for j, jt in enumerate(m["joints"]):
+        p = p + R @ np.array(jt["xyz"])
+        c, s = np.cos(q[j]), np.sin(q[j])
+        R = R @ rpy(*jt["rpy"]) @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+        frames.append((R.copy(), p.copy(), jt["mass"], np.array(jt["com"])))
+    return frames
+
+
+@pytest.mark.parametrize("robot,name", [(0, "kuka_iiwa"), (1, "diana_s1")])
+def test_aba_matches_dense_route_and_rnea(oracle, robot, name):
+    """two independent algorithms (Featherstone ABA vs M^-1(tau - h) from recursive Newton-Euler) agree to 1e-9;
+    RNEA(q, qd, ABA(q, qd, tau)) returns tau; M is symmetric positive definite"""
+    rng = np.random.default_rng(robot)
+    for _ in range(100):
+        q, qd, tau = rng.uniform(-2.5, 2.5, 7), rng.uniform(-3, 3, 7), rng.uniform(-100, 100, 7)
+        a = oracle.aba(q, qd, tau, robot)
+        b, M = oracle.dense_fd(q, qd, tau, robot)
+        assert np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(b).max())
+        assert np.abs(M - M.T).max() <= 1e-12 and np.linalg.eigvalsh(M).min() > 0
+        assert np.abs(oracle.rnea(q, qd, a, robot) - tau).max() <= 1e-9
+
+
+@pytest.mark.parametrize("robot,name", [(0, "kuka_iiwa"), (1, "diana_s1")])
+def test_aba_gravity_torque_is_the_potential_gradient(oracle, robot, name):
+    """g(q) = RNEA(q, 0, 0) equals d/dq of sum_i m_i g z_com_i computed by an independent numpy FK; holding the arm
+    with exactly that torque gives zero acceleration"""
+    rng = np.random.default_rng(5)
+
+    def pot(q):
+        return sum(m * 10.0 * (p + R @ c)[2] for R, p, m, c in _numpy_link_frames(name, q))
+    for _ in range(10):
+        q = rng.uniform(-2, 2, 7)
+        g = oracle.rnea(q, np.zeros(7), np.zeros(7), robot)
+        num = np.array([(pot(q + 1e-6 * np.eye(7)[j]) - pot(q - 1e-6 * np.eye(7)[j])) / 2e-6 for j in range(7)])
+        assert np.abs(g - num).max() <= 1e-6 * max(1.0, np.abs(g).max())
+        assert np.abs(oracle.aba(q, np.zeros(7), g, robot)).max() <= 1e-9
+
+
+def test_aba_conserves_energy_without_damping(oracle):
+    """DianaS1 has zero joint damping (DianaS1_robot.urdf:35): free swing under gravity keeps kinetic + potential
+    energy (RK4 on the ABA accelerations; potential from the independent numpy FK)"""
+    rng = np.random.default_rng(2)
+    q, qd = rng.uniform(-1, 1, 7), rng.uniform(-0.5, 0.5, 7)
+
+    def energy(q, qd):
+        _, M = oracle.dense_fd(q, qd, np.zeros(7), 1)
+        return 0.5 * qd @ M @ qd + sum(m * 10.0 * (p + R @ c)[2] for R, p, m, c in _numpy_link_frames("diana_s1", q))
+
+    def f(q, qd):
+        return qd, oracle.aba(q, qd, np.zeros(7), 1)
+    e0 = energy(q, qd)
+    h = 1e-3
+    for _ in range(300):
+        k1 = f(q, qd); k2 = f(q + 0.5 * h * k1[0], qd + 0.5 * h * k1[1])
+        k3 = f(q + 0.5 * h * k2[0], qd + 0.5 * h * k2[1]); k4 = f(q + h * k3[0], qd + h * k3[1])
+        q = q + h / 6 * (k1[0] + 2 * k2[0] + 2 * k3[0] + k4[0])
+        qd = qd + h / 6 * (k1[1] + 2 * k2[1] + 2 * k3[1] + k4[1])
+    assert abs(energy(q, qd) - e0) <= 1e-6 * max(1.0, abs(e0))
+
+
+def test_torque_mode_step_semantics(oracle):
+    """effort clip, velocity clip, joint-limit clamp with the velocity zeroed, obs = [task obs, q, qd]"""
+    cfg = oracle.default_config(0, n_envs=2, mode=oracle.MODE_TORQUE)
+    sim = oracle.OracleSim(cfg)
+    assert sim.act_dim == 7 and sim.obs_dim == 6 + 14
+    o0 = sim.reset()
+    assert np.allclose(o0[:, 6:13], np.array(cfg.init_q[:], np.float32)) and np.all(o0[:, 13:] == 0)
+    a = np.zeros((2, 7), np.float32)
+    a[0] = 1e6                                       # way beyond the 300 N m effort limit
+    a[1] = -1e6
+    for k in range(400):
+        o, r, d, s = sim.step(a)
+    q, qd = sim.get_state_f64(oracle.F_Q), sim.get_state_f64(oracle.F_QD)
+    up = np.array([2.96705972839, 2.09439510239, 2.96705972839, 2.09439510239, 2.96705972839, 2.09439510239, 3.05432619099])
+    assert np.all(np.abs(q) <= up + 1e-12) and np.all(np.abs(qd) <= 10.0 + 1e-12)
+    at_lim = np.abs(np.abs(q) - up) < 1e-12
+    assert at_lim.any() and np.all(qd[at_lim] * np.sign(q[at_lim]) <= 0)          # no velocity into the stop
+    assert np.allclose(o[:, 6:13], q, atol=1e-6) and np.allclose(o[:, 13:], qd, atol=1e-5)
+    assert np.all(r <= 0) and not d.any()
+    sim.close()

@@ -470,3 +470,81 @@ def test_drop_in_env_classes(pkg, torch_cuda, name, odim, dtype):
     else:
         assert set(info) == {"is_success"} and info["is_success"].dtype == np.float32
     env.close()
+
+
+# --------------------------------------------------------------------------------------------- torque mode (ABA)
+@pytest.mark.parametrize("robot,rid", [("kuka_iiwa", 0), ("diana_s1", 1)])
+def test_torque_step_teacher_forced(pkg, oracle, torch_cuda, robot, rid):
+    """one ABA + integration step from identical (q, qd, tau): fp32 kernel vs fp64 oracle.
+    Tolerance: |dqd| <= 2e-4 rad/s (qdd up to ~1e3 rad/s^2 times dt, fp32 ABA), |dq| <= 2e-6 rad, |dee| <= 5e-6 m"""
+    L, O = pkg._lib, oracle
+    n = 1024
+    env = pkg.ArmSimHandle("reach", n_envs=n, seed=2, robot=robot, mode="torque")
+    ora = O.OracleSim(O.default_config(0, n_envs=n, seed=2, robot=rid, mode=O.MODE_TORQUE))
+    assert env.act_dim == 7 and env.obs_dim == 20 and ora.obs_dim == 20
+    rng = np.random.default_rng(8)
+    for k in range(6):
+        q = rng.uniform(-1.8, 1.8, (n, 7)).astype(np.float32)
+        qd = rng.uniform(-2.0, 2.0, (n, 7)).astype(np.float32)
+        tau = rng.uniform(-120, 120, (n, 7)).astype(np.float32)
+        if k == 5:
+            tau *= 10                                                  # saturate the effort clip
+        for s in (env, ora):
+            s.set_state(L.F_Q, q); s.set_state(L.F_QD, qd)
+        og, rg, dg, sg = env.step_host(tau)
+        oo, ro, do, so = ora.step(tau)
+        dqd = np.abs(env.get_state(L.F_QD) - ora.get_state_f64(O.F_QD))
+        dq = np.abs(env.get_state(L.F_Q) - ora.get_state_f64(O.F_Q))
+        assert dqd.max() <= 2e-4, dqd.max()
+        assert dq.max() <= 2e-6, dq.max()
+        assert np.abs(og[:, :3] - oo[:, :3]).max() <= 5e-6
+        assert np.array_equal(og[:, 3:6], oo[:, 3:6])
+        assert np.abs(og[:, 6:] - oo[:, 6:]).max() <= 2e-4
+        assert np.abs(rg - ro).max() <= 1e-4 and np.array_equal(dg, do)
+    env.close(); ora.close()
+
+
+def test_torque_free_running_and_limits(pkg, oracle, torch_cuda):
+    """200 free-running steps under random bounded torques stay close to the oracle; saturated torques run into the
+    joint stops and are held there with no velocity into the stop"""
+    L, O = pkg._lib, oracle
+    n = 256
+    env = pkg.ArmSimHandle("reach", n_envs=n, seed=4, mode="torque")
+    ora = O.OracleSim(O.default_config(0, n_envs=n, seed=4, mode=O.MODE_TORQUE))
+    rng = np.random.default_rng(1)
+    g0 = np.stack([O.rnea(np.array(env.cfg.init_q[:]), np.zeros(7), np.zeros(7))] * n).astype(np.float32)
+    for k in range(200):
+        tau = g0 + rng.uniform(-3, 3, (n, 7)).astype(np.float32)       # hover around gravity compensation
+        og, *_ = env.step_host(tau)
+        oo, *_ = ora.step(tau)
+    assert np.abs(env.get_state(L.F_Q) - ora.get_state_f64(O.F_Q)).max() <= 2e-3
+    assert np.abs(og[:, :3] - oo[:, :3]).max() <= 2e-3
+    tau = np.full((n, 7), 1e6, np.float32)
+    for k in range(400):
+        og, rg, dg, sg = env.step_host(tau)
+    q, qd = env.get_state(L.F_Q), env.get_state(L.F_QD)
+    up = np.array([2.96705972839, 2.09439510239, 2.96705972839, 2.09439510239, 2.96705972839, 2.09439510239, 3.05432619099], np.float32)
+    assert np.all(np.abs(q) <= up + 1e-6) and np.all(np.abs(qd) <= 10.0 + 1e-5)
+    at = np.abs(q - up) < 1e-6
+    assert at.any() and np.all(qd[at] <= 0)
+    env.close(); ora.close()
+
+
+@pytest.mark.parametrize("task,tid,od", [("push", 1, 23), ("pick", 2, 23), ("kuka_reach", 3, 17)])
+def test_torque_mode_other_tasks(pkg, oracle, torch_cuda, task, tid, od):
+    """torque mode under the other task epilogues (cube contact, pick gripper, sparse reward), incl. auto-reset"""
+    L, O = pkg._lib, oracle
+    n = 300
+    env = pkg.ArmSimHandle(task, n_envs=n, seed=6, mode="torque", auto_reset=True, max_steps=20)
+    ora = O.OracleSim(O.default_config(tid, n_envs=n, seed=6, mode=O.MODE_TORQUE, auto_reset=1, max_steps=20))
+    assert env.obs_dim == od
+    rng = np.random.default_rng(3)
+    for k in range(45):                                                  # crosses two auto-resets
+        tau = rng.uniform(-40, 40, (n, 7)).astype(np.float32)
+        og, rg, dg, sg = env.step_host(tau)
+        oo, ro, do, so = ora.step(tau)
+        assert np.array_equal(dg, do), k
+        assert np.abs(og - oo).max() <= 5e-3, (k, np.abs(og - oo).max())
+        assert np.array_equal(env.get_state(L.F_STEP), ora.get_state(O.F_STEP))
+    assert dg.sum() == 0 and np.array_equal(env.get_state(L.F_EPISODE), ora.get_state(O.F_EPISODE))
+    env.close(); ora.close()
