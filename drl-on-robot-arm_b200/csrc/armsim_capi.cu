@@ -156,6 +156,35 @@ static void* field_ptr(ArmSim* s, int32_t f) {
   }
 }
 
+// Step kernels go out with the programmatic-stream-serialization attribute (programmatic dependent launch): a step
+// launched right behind another kernel of the stream is scheduled onto idle SMs while that kernel still runs and
+// parks in griddepcontrol.wait (first instruction of the kernel, before any global read) until the predecessor has
+// completed and flushed -- the ~1 us launch gap between back-to-back steps overlaps the previous step's tail.
+// ARMSIM_PDL=0 in the environment turns it off.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ARMSIM_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <class... KArgs, class... Args>
+static void launch_k(void (*kern)(KArgs...), int grid, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(LANE_BLOCK);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 extern "C" {
 
 int32_t armsim_abi_version(void) { return ARMSIM_ABI_VERSION; }
@@ -203,12 +232,12 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
 // the parameter-driven one
 #define ARMSIM_STEP_CASE(TASK, ROBOT)                                                                           \
   case (TASK) * 4 + (ROBOT):                                                                                    \
-    step_lane_kernel<TASK, ROBOT><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, a, o, r, d, su, H);     \
+    launch_k(step_lane_kernel<TASK, ROBOT>, grid, st, H.flag == nullptr, s->chain, s->task, s->S, a, o, r, d, su, H); \
     break;
 
 #define ARMSIM_TORQUE_CASE(TASK, ROBOT)                                                                                \
   case (TASK) * 4 + (ROBOT):                                                                                           \
-    step_torque_kernel<TASK, ROBOT><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->dyn, s->S, a, o, r, d, su, H);  \
+    launch_k(step_torque_kernel<TASK, ROBOT>, grid, st, H.flag == nullptr, s->chain, s->task, s->dyn, s->S, a, o, r, d, su, H); \
     break;
 
 static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st,

@@ -240,6 +240,11 @@ struct HostNotify {
   unsigned int seq;
 };
 
+// Programmatic dependent launch (see launch_k in armsim_capi.cu): nothing may be read from global memory before
+// pdl_wait(); pdl_release() lets the next PDL-launched kernel of the stream start its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void notify_host(const HostNotify& H) {
   if (H.flag == nullptr) return;
   __threadfence_system();                 // this thread's output stores are visible to the host ...
@@ -268,6 +273,8 @@ step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ 
   __shared__ float s_io[LANE_BLOCK / 32][STAGE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wbase = blockIdx.x * LANE_BLOCK + warp * 32;
+  pdl_wait();
+  pdl_release();
   if (wbase < T.n) {
     const int cnt = min(32, T.n - wbase);
     const bool live = lane < cnt;
@@ -322,6 +329,8 @@ step_torque_kernel(const __grid_constant__ ChainParams C, const __grid_constant_
   __shared__ float s_io[LANE_BLOCK / 32][32 * OD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wbase = blockIdx.x * LANE_BLOCK + warp * 32;
+  pdl_wait();
+  pdl_release();
   if (wbase < T.n) {
     const int n = T.n;
     const int cnt = min(32, n - wbase);
