@@ -34,6 +34,17 @@ METRIC = "env-steps/sec (reach, N_envs=4096)"
 UNIT = "env-steps/s"
 
 
+def load_traffic(task, n):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None"""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
+    try:
+        d = json.load(open(p))["v3_%s_n%d" % (task, n)]
+        return d["dram__bytes_read.sum"]["value"] * {"Kbyte": 1e3, "Mbyte": 1e6, "byte": 1.0}[d["dram__bytes_read.sum"]["unit"]] + \
+            d["dram__bytes_write.sum"]["value"] * {"Kbyte": 1e3, "Mbyte": 1e6, "byte": 1.0}[d["dram__bytes_write.sum"]["unit"]]
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -327,7 +338,9 @@ def run_ours(args):
                              "(%.0f MB touched state, L2 = 126 MB), every launch HBM-cold" % (pool, n, pool * abytes * n / 1e6),
                        "launch": "CUDA graph of exactly K fused-step launches, CUDA events on the launching stream"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
+                         "traffic": load_traffic(task, n), "traffic_unit": "bytes per launch (dram read + write, ncu --set full, "
+                         "profiles/r01_ncu_summary.json; writes still in L2 at kernel end are not counted by ncu)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
                          "kernel": "step_lane_kernel<%s>" % task, "avg_launch_us": launch_us,
                          "note": "kernel is fp32-issue / launch-latency bound, not HBM bound (SURVEY 7): ~6 kFLOP of "
                                  "dependent fp32 per 118 B"},
