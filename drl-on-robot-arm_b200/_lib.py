@@ -23,7 +23,9 @@ EXPORTS = [
     "armsim_abi_version", "armsim_last_error", "armsim_default_config", "armsim_create", "armsim_destroy",
     "armsim_reset", "armsim_step", "armsim_step_host", "armsim_reset_host", "armsim_set_state", "armsim_get_state",
     "armsim_obs_dim", "armsim_action_dim", "armsim_n_envs", "armsim_mapping", "armsim_launch_count", "armsim_fk_host",
-    "armsim_host_buffers",
+    "armsim_host_buffers", "armsim_step_ex",
+    "armsim_replay_create", "armsim_replay_destroy", "armsim_replay_begin", "armsim_replay_store", "armsim_replay_sample",
+    "armsim_replay_gather", "armsim_replay_info", "armsim_replay_table", "armsim_replay_last_error",
 ]
 
 
@@ -48,6 +50,13 @@ class ArmsimConfig(C.Structure):
                 ("clamp_joint_limits", C.c_int32), ("reserved", C.c_int32 * 7),
                 ("sim_dt", C.c_double), ("gravity", C.c_double * 3),
                 ("custom_chain", C.POINTER(ArmsimChain))]
+
+
+class ArmReplayConfig(C.Structure):
+    """include/armsim.h ArmReplayConfig."""
+    _fields_ = [("struct_size", C.c_int32), ("n_envs", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32),
+                ("window", C.c_int32), ("table_cap", C.c_int32), ("kind", C.c_int32), ("device", C.c_int32),
+                ("seed", C.c_uint64)]
 
 
 class ArmsimError(RuntimeError):
@@ -79,6 +88,7 @@ def lib():
     L.armsim_reset.argtypes = [vp, vp, vp, vp]
     L.armsim_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.armsim_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.armsim_step_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.armsim_reset_host.argtypes = [vp, vp, vp]
     L.armsim_host_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
     L.armsim_set_state.argtypes = [vp, i32, vp, C.c_size_t]
@@ -89,6 +99,16 @@ def lib():
     L.armsim_launch_count.argtypes = [vp]
     L.armsim_launch_count.restype = C.c_int64
     L.armsim_fk_host.argtypes = [vp, vp, i32, vp, vp]
+    L.armsim_replay_create.argtypes = [C.POINTER(ArmReplayConfig), C.POINTER(vp)]
+    L.armsim_replay_destroy.argtypes = [vp]
+    L.armsim_replay_destroy.restype = None
+    L.armsim_replay_begin.argtypes = [vp, vp, vp]
+    L.armsim_replay_store.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.armsim_replay_sample.argtypes = [vp, i32, i32, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]
+    L.armsim_replay_gather.argtypes = [vp, i32, vp, vp, vp, C.c_float, vp, vp, vp, vp, vp, vp]
+    L.armsim_replay_info.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.armsim_replay_table.argtypes = [vp, vp, vp, vp, i32]
+    L.armsim_replay_last_error.restype = C.c_char_p
     if L.armsim_abi_version() != 2:
         raise ArmsimError("libarmsim ABI version %d != 2" % L.armsim_abi_version())
     _lib = L
@@ -98,6 +118,11 @@ def lib():
 def check(rc):
     if rc != 0:
         raise ArmsimError("libarmsim error %d: %s" % (rc, lib().armsim_last_error().decode()))
+
+
+def check_replay(rc):
+    if rc != 0:
+        raise ArmsimError("libarmsim replay error %d: %s" % (rc, lib().armsim_replay_last_error().decode()))
 
 
 def default_config(task, **overrides):

@@ -232,16 +232,16 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
 // the parameter-driven one
 #define ARMSIM_STEP_CASE(TASK, ROBOT)                                                                           \
   case (TASK) * 4 + (ROBOT):                                                                                    \
-    launch_k(step_lane_kernel<TASK, ROBOT>, grid, st, H.flag == nullptr, s->chain, s->task, s->S, a, o, r, d, su, H); \
+    launch_k(step_lane_kernel<TASK, ROBOT>, grid, st, H.flag == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     break;
 
 #define ARMSIM_TORQUE_CASE(TASK, ROBOT)                                                                                \
   case (TASK) * 4 + (ROBOT):                                                                                           \
-    launch_k(step_torque_kernel<TASK, ROBOT>, grid, st, H.flag == nullptr, s->chain, s->task, s->dyn, s->S, a, o, r, d, su, H); \
+    launch_k(step_torque_kernel<TASK, ROBOT>, grid, st, H.flag == nullptr, s->chain, s->task, s->dyn, s->S, a, o, r, d, su, fo, H); \
     break;
 
 static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st,
-                       const HostNotify H = HostNotify{nullptr, nullptr, 0u}) {
+                       const HostNotify H = HostNotify{nullptr, nullptr, 0u}, float* fo = nullptr) {
   const int grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
   if (s->cfg.mode == ARMSIM_MODE_TORQUE) {
     switch (s->cfg.task * 4 + s->cfg.robot) {
@@ -426,6 +426,14 @@ int armsim_host_buffers(ArmSim* s, float** action, float** obs, float** reward, 
   if (done) *done = (uint8_t*)(h_out + s->off_done);
   if (success) *success = (uint8_t*)(h_out + s->off_success);
   return ARMSIM_OK;
+}
+
+int armsim_step_ex(ArmSim* s, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev,
+                   float* final_obs_dev, void* stream) {
+  if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_ex: null handle");
+  if (!action_dev || !obs_dev || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_step_ex: null buffer");
+  return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream, HostNotify{nullptr, nullptr, 0u},
+                     final_obs_dev);
 }
 
 int armsim_step_host(ArmSim* s, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host,

@@ -186,7 +186,7 @@ __device__ __forceinline__ void mat_to_quat(const float (&m)[9], float (&q)[4]) 
 // Bullet (IKTrajectoryHelper::computeIK) forms it as 2*acos(w) * v/sqrt(1-w^2); for a unit quaternion that is
 // 2*atan2(|v|, w) * v/|v|, which is the form used here because it stays well-conditioned in fp32 when the error is
 // small (acos near 1 loses half the mantissa).
-__device__ __noinline__ void rot_error_quat(const float (&tq)[4], const float (&R)[9], float (&e)[3]) {
+static __device__ __noinline__ void rot_error_quat(const float (&tq)[4], const float (&R)[9], float (&e)[3]) {
   float sq[4];
   mat_to_quat(R, sq);
   const float ix = -sq[0], iy = -sq[1], iz = -sq[2], iw = sq[3];

@@ -147,7 +147,8 @@ __device__ __forceinline__ void load_env(const TaskParams& T, const StatePtrs& S
 template <int TASK>
 __device__ __forceinline__ bool task_epilogue(const ChainParams& C, const TaskParams& T, const StatePtrs& S, int e, bool live,
                                               EnvRegs<TASK>& E, const float (&p)[3], const float (&R)[9], int its,
-                                              float (&o)[TaskTraits<TASK>::OBS], float& r, uint8_t& d, uint8_t& su) {
+                                              float (&o)[TaskTraits<TASK>::OBS], float (&of)[TaskTraits<TASK>::OBS],
+                                              float& r, uint8_t& d, uint8_t& su) {
   const int n = T.n;
   float (&q)[NJ] = E.q;
   float (&goal)[3] = E.goal;
@@ -203,14 +204,16 @@ __device__ __forceinline__ bool task_epilogue(const ChainParams& C, const TaskPa
   }
   d = term ? 1 : 0;
   su = succ ? 1 : 0;
-  if (!live) { make_obs<TASK>(p, goal, cb, o); return false; }
+  make_obs<TASK>(p, goal, cb, of);                 // the observation of THIS step (gymnasium's final_observation)
+#pragma unroll
+  for (int k = 0; k < TaskTraits<TASK>::OBS; ++k) o[k] = of[k];
+  if (!live) return false;
   S.step[e] = stepc;
   if (term && T.auto_reset) {
-    reset_env<TASK>(C, T, S, e, o);
+    reset_env<TASK>(C, T, S, e, o);                // obs = first observation of the next episode
     return true;
   }
   if (term) S.done[e] = 1;
-  make_obs<TASK>(p, goal, cb, o);
   return false;
 }
 
@@ -219,16 +222,18 @@ __device__ __forceinline__ bool task_epilogue(const ChainParams& C, const TaskPa
 template <int TASK, int ROBOT>
 __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams& T, const StatePtrs& S, int e, bool live,
                                          EnvRegs<TASK>& E, const float (&a)[3], float (&o)[TaskTraits<TASK>::OBS],
-                                         float& r, uint8_t& d, uint8_t& su) {
+                                         float (&of)[TaskTraits<TASK>::OBS], float& r, uint8_t& d, uint8_t& su) {
   float p[3], R[9];
   const bool frozen = E.latched != 0;               // finished env waiting for reset: report its frozen state
   const int its = servo_core<ROBOT, TASK != ARMSIM_TASK_KUKA_REACH>(C, T, a, frozen, E.q, p, R);
   if (frozen) {
     make_obs<TASK>(p, E.goal, E.cb, o);
+#pragma unroll
+    for (int k = 0; k < TaskTraits<TASK>::OBS; ++k) of[k] = o[k];
     r = 0.f; d = 1; su = 0;
     return;
   }
-  task_epilogue<TASK>(C, T, S, e, live, E, p, R, its, o, r, d, su);
+  task_epilogue<TASK>(C, T, S, e, live, E, p, R, its, o, of, r, d, su);
 }
 
 // Completion doorbell of the host-buffer path (armsim_step_host): when `flag` is non-null the kernel's outputs go
@@ -267,7 +272,8 @@ template <int TASK, int ROBOT>
 __global__ void __launch_bounds__(LANE_BLOCK)
 step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T, const StatePtrs S,
                  const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
-                 uint8_t* __restrict__ done, uint8_t* __restrict__ success, const HostNotify H) {
+                 uint8_t* __restrict__ done, uint8_t* __restrict__ success, float* __restrict__ final_obs,
+                 const HostNotify H) {
   constexpr int OD = TaskTraits<TASK>::OBS;
   constexpr int STAGE = 32 * (OD > 3 ? OD : 3);
   __shared__ float s_io[LANE_BLOCK / 32][STAGE];
@@ -296,9 +302,9 @@ step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ 
     const float a[3] = {st[al], st[al + 1], st[al + 2]};
     __syncwarp();
 
-    float o[OD], r;
+    float o[OD], of[OD], r;
     uint8_t d, su;
-    step_env<TASK, ROBOT>(C, T, S, e, live, E, a, o, r, d, su);
+    step_env<TASK, ROBOT>(C, T, S, e, live, E, a, o, of, r, d, su);
     if (live) {
       reward[e] = r;
       done[e] = d;
@@ -312,6 +318,17 @@ step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ 
       const int i = k * 32 + lane;
       if (i < cnt * OD) obs[(size_t)wbase * OD + i] = st[i];
     }
+    if (final_obs != nullptr) {        // second pass through the same staging slice
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < OD; ++k) st[lane * OD + k] = of[k];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < OD; ++k) {
+        const int i = k * 32 + lane;
+        if (i < cnt * OD) final_obs[(size_t)wbase * OD + i] = st[i];
+      }
+    }
   }
   notify_host(H);
 }
@@ -323,7 +340,7 @@ __global__ void __launch_bounds__(LANE_BLOCK)
 step_torque_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T,
                    const __grid_constant__ DynParams Dn, const StatePtrs S, const float* __restrict__ action,
                    float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
-                   uint8_t* __restrict__ success, const HostNotify H) {
+                   uint8_t* __restrict__ success, float* __restrict__ final_obs, const HostNotify H) {
   constexpr int OB = TaskTraits<TASK>::OBS;
   constexpr int OD = OB + 2 * NJ;
   __shared__ float s_io[LANE_BLOCK / 32][32 * OD];
@@ -357,7 +374,7 @@ step_torque_kernel(const __grid_constant__ ChainParams C, const __grid_constant_
     for (int k = 0; k < NJ; ++k) cmd[k] = st[al + k];
     __syncwarp();
 
-    float o[OB], r = 0.f, p[3], R[9], P[NJ][3], Z[NJ][3];
+    float o[OB], of[OB], r = 0.f, p[3], R[9], P[NJ][3], Z[NJ][3];
     uint8_t d = 1, su = 0;
     bool was_reset = false;
     const bool frozen = E.latched != 0;
@@ -365,12 +382,14 @@ step_torque_kernel(const __grid_constant__ ChainParams C, const __grid_constant_
     RobotFK<ROBOT>::template run<false>(C, E.q, p, R, P, Z);
     if (frozen) {
       make_obs<TASK>(p, E.goal, E.cb, o);
+#pragma unroll
+      for (int k = 0; k < OB; ++k) of[k] = o[k];
     } else {
       if (live) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) S.qd[j * n + e] = E.qd[j];
       }
-      was_reset = task_epilogue<TASK>(C, T, S, e, live, E, p, R, 0, o, r, d, su);
+      was_reset = task_epilogue<TASK>(C, T, S, e, live, E, p, R, 0, o, of, r, d, su);
     }
     if (live) {
       reward[e] = r;
@@ -389,6 +408,19 @@ step_torque_kernel(const __grid_constant__ ChainParams C, const __grid_constant_
     for (int k = 0; k < OD; ++k) {
       const int i = k * 32 + lane;
       if (i < cnt * OD) obs[(size_t)wbase * OD + i] = st[i];
+    }
+    if (final_obs != nullptr) {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < OB; ++k) st[lane * OD + k] = of[k];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { st[lane * OD + OB + j] = E.q[j]; st[lane * OD + OB + NJ + j] = E.qd[j]; }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < OD; ++k) {
+        const int i = k * 32 + lane;
+        if (i < cnt * OD) final_obs[(size_t)wbase * OD + i] = st[i];
+      }
     }
   }
   notify_host(H);

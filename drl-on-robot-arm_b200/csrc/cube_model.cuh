@@ -161,7 +161,7 @@ __device__ __forceinline__ void row(State& cb, const float (&r)[3], const float 
 }
 
 // one p.stepSimulation() for the cube; grip: 0 open / push, 1 closed, 2 holding
-__device__ __noinline__ void step(State& cb, const float (&ee)[3], const float (&Ree)[9], bool pick, float grip) {
+static __device__ __noinline__ void step(State& cb, const float (&ee)[3], const float (&Ree)[9], bool pick, float grip) {
   if (pick && grip >= 1.5f) {
     cb.pos[0] = ee[0] + GRIPPER_LEN * Ree[2];
     cb.pos[1] = ee[1] + GRIPPER_LEN * Ree[5];

@@ -169,14 +169,24 @@ class BatchedArmEnv(ArmSimHandle):
         L.check(L.lib().armsim_reset(self.h, m, self.obs.data_ptr(), self._stream()))
         return self.obs
 
-    def step(self, action, out=None):
-        """action: float32 CUDA tensor [N, 3].  Returns (obs, reward, done, success) views of the env's own output
-        buffers (overwritten by the next step) unless `out` = (obs, reward, done, success) tensors is given."""
+    def step(self, action, out=None, final_obs=None):
+        """action: float32 CUDA tensor [N, act_dim].  Returns (obs, reward, done, success) views of the env's own
+        output buffers (overwritten by the next step) unless `out` = (obs, reward, done, success) tensors is given.
+        final_obs (optional f32 [N, obs_dim] tensor, or True for the env's own buffer `self.final_obs`) receives this
+        step's observation before any in-kernel auto-reset (what a replay buffer stores as next_state)."""
         t = self.torch
         if action.dtype != t.float32 or not action.is_cuda or not action.is_contiguous() or \
                 tuple(action.shape) != (self.n, self.act_dim):
             action = action.to(device=self.device, dtype=t.float32).reshape(self.n, self.act_dim).contiguous()
         obs, rew, done, succ = out if out is not None else (self.obs, self.reward, self.done, self.success)
-        L.check(L.lib().armsim_step(self.h, action.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
-                                    succ.data_ptr(), self._stream()))
+        if final_obs is None:
+            L.check(L.lib().armsim_step(self.h, action.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                        succ.data_ptr(), self._stream()))
+        else:
+            if final_obs is True:
+                if getattr(self, "final_obs", None) is None:
+                    self.final_obs = t.empty_like(self.obs)
+                final_obs = self.final_obs
+            L.check(L.lib().armsim_step_ex(self.h, action.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                           succ.data_ptr(), final_obs.data_ptr(), self._stream()))
         return obs, rew, done, succ

@@ -136,6 +136,12 @@ int armsim_reset(ArmSim* sim, const uint8_t* mask_dev, float* obs_dev, void* str
 int armsim_step(ArmSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                 uint8_t* success_dev, void* stream);
 
+/* armsim_step plus one more output: final_obs_dev f32 [n, obs_dim] (nullable) receives the observation of THIS step
+ * before any in-kernel auto-reset -- what the reference's step() returns on a terminal step (rl_reach_env.py:319)
+ * and what a replay buffer must store as next_state; equal to obs_dev for envs that did not terminate. */
+int armsim_step_ex(ArmSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                   uint8_t* success_dev, float* final_obs_dev, void* stream);
+
 /* Same step through HOST buffers (what a host-side Env.step sees): the actions cross to the device, the fused
  * launch runs, obs/reward/done/success cross back, and the call returns when they are in the caller's buffers.
  * Arbitrary host pointers are staged through the handle's pinned block; see armsim_host_buffers for the copy-free
@@ -168,6 +174,53 @@ const char* armsim_last_error(void);
  * on the device by the same routine the step kernel uses.  Synchronous; for tests and for Env shims that need
  * getLinkState-style queries. */
 int armsim_fk_host(ArmSim* sim, const float* q_host, int32_t n, float* pos_host, float* rot_host);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Trajectory replay with HER "future" relabelling, resident in HBM.  Replaces utils/rl_utils.py:91-105 (Trajectory)
+ * and :108-199 (ReplayBuffer_Trajectory_reach / _push: add_trajectory, size, sample) for the lockstep batch: every
+ * env step appends ONE row for all n envs; an episode becomes sampleable when its terminal step is stored (the
+ * reference adds a trajectory at episode end, main.py:129).  All cursors live on the device: store / sample are
+ * asynchronous on `stream` and CUDA-graph capturable.
+ */
+typedef struct ArmReplay ArmReplay;
+typedef struct ArmReplayConfig {
+  int32_t struct_size;   /* = sizeof(ArmReplayConfig) */
+  int32_t n_envs;        /* envs of this shard (rows are [n_envs, ...]) */
+  int32_t obs_dim;       /* >= 6: obs[0:3] = achieved position (EE), obs[3:6] = goal slot (rl_utils.py:134,140) */
+  int32_t act_dim;
+  int32_t window;        /* ring length in lockstep steps; episodes longer than this are dropped */
+  int32_t table_cap;     /* trajectory-table slots (the reference's deque capacity, counted in trajectories) */
+  int32_t kind;          /* 0 = reach relabelling (rl_utils.py:133-141), 1 = push (:180-188) */
+  int32_t device;
+  uint64_t seed;         /* Philox key of the sampler */
+} ArmReplayConfig;
+
+int armsim_replay_create(const ArmReplayConfig* cfg, ArmReplay** out);
+void armsim_replay_destroy(ArmReplay* rep);
+/* Start (or restart) every env's episode at the current row with obs0_dev f32 [n, obs_dim] as states[0]
+ * (Trajectory(init_state), rl_utils.py:93-94).  Call after Env.reset() and before the first store. */
+int armsim_replay_begin(ArmReplay* rep, const float* obs0_dev, void* stream);
+/* Append the row of one lockstep Env.step (Trajectory.store_step, rl_utils.py:100-105): action [n,A], reward [n],
+ * done u8 [n], final_obs [n,O] (this step's observation before auto-reset, armsim_step_ex) and obs_out [n,O] (the
+ * observation the next step starts from).  Envs with done != 0 commit their trajectory (add_trajectory, :112). */
+int armsim_replay_store(ArmReplay* rep, const float* action_dev, const float* reward_dev, const uint8_t* done_dev,
+                        const float* final_obs_dev, const float* obs_out_dev, void* stream);
+/* sample(batch_size, use_her, dis_threshold, her_ratio) (rl_utils.py:119-152 / :165-199): states [B,O], actions
+ * [B,A], next_states [B,O], rewards [B], dones f32 0/1 [B].  picks_dev i32 [B,3] (nullable) receives the drawn
+ * (table slot, step, goal step or -1).  Needs at least one committed trajectory. */
+int armsim_replay_sample(ArmReplay* rep, int32_t batch, int32_t use_her, float dis_threshold, float her_ratio,
+                         float* states_dev, float* actions_dev, float* next_states_dev, float* rewards_dev,
+                         float* dones_dev, int32_t* picks_dev, void* stream);
+/* The same transition builder for EXPLICIT picks (slot, step, goal_step or -1): the deterministic entry the parity
+ * tests use against the reference's relabelling. */
+int armsim_replay_gather(ArmReplay* rep, int32_t batch, const int32_t* slot_dev, const int32_t* step_dev,
+                         const int32_t* goal_step_dev, float dis_threshold, float* states_dev, float* actions_dev,
+                         float* next_states_dev, float* rewards_dev, float* dones_dev, void* stream);
+/* Synchronous read-backs: info = {rows stored, trajectories committed (size(), rl_utils.py:115), sample calls};
+ * the first `count` trajectory-table entries (env, absolute start row, length). */
+int armsim_replay_info(ArmReplay* rep, int64_t info[3]);
+int armsim_replay_table(ArmReplay* rep, int32_t* env_host, int64_t* start_host, int32_t* len_host, int32_t count);
+const char* armsim_replay_last_error(void);
 
 #ifdef __cplusplus
 }
