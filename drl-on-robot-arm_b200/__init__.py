@@ -3,7 +3,7 @@
 Import name: `drl_on_robot_arm_b200` (see drl_on_robot_arm_b200.py at the repo root; the directory keeps the
 hyphenated project name).  Compute happens only in libarmsim.so (hand-written sm_100a CUDA behind include/armsim.h).
 """
-from . import _build, _lib, config, envs, replay, spaces
+from . import _build, _lib, config, envs, metrics, replay, spaces
 from ._lib import ArmsimError
 from .config import opt
 from .replay import TrajectoryReplay

@@ -26,6 +26,7 @@ EXPORTS = [
     "armsim_host_buffers", "armsim_step_ex",
     "armsim_replay_create", "armsim_replay_destroy", "armsim_replay_begin", "armsim_replay_store", "armsim_replay_sample",
     "armsim_replay_gather", "armsim_replay_info", "armsim_replay_table", "armsim_replay_last_error",
+    "armsim_replay_state_bytes", "armsim_replay_get_state", "armsim_replay_set_state",
 ]
 
 
@@ -109,6 +110,10 @@ def lib():
     L.armsim_replay_info.argtypes = [vp, C.POINTER(C.c_int64)]
     L.armsim_replay_table.argtypes = [vp, vp, vp, vp, i32]
     L.armsim_replay_last_error.restype = C.c_char_p
+    L.armsim_replay_state_bytes.argtypes = [vp]
+    L.armsim_replay_state_bytes.restype = C.c_int64
+    L.armsim_replay_get_state.argtypes = [vp, vp, C.c_int64]
+    L.armsim_replay_set_state.argtypes = [vp, vp, C.c_int64]
     if L.armsim_abi_version() != 2:
         raise ArmsimError("libarmsim ABI version %d != 2" % L.armsim_abi_version())
     _lib = L

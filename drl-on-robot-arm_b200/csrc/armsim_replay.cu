@@ -51,6 +51,7 @@ struct ReplayDev {
 struct ArmReplay {
   ReplayDev d{};
   void* block = nullptr;
+  size_t bytes = 0;
   int device = 0;
 };
 
@@ -233,6 +234,7 @@ int armsim_replay_create(const ArmReplayConfig* cfg, ArmReplay** out) {
     return rfail(ARMSIM_E_NOMEM, "armsim_replay_create: cudaMalloc of %zu bytes failed", total);
   }
   cudaMemset(r->block, 0, total);
+  r->bytes = total;
   char* p = (char*)r->block;
   d.act = (float*)p; p += b_act;
   d.rew = (float*)p; p += b_rew;
@@ -306,6 +308,25 @@ int armsim_replay_info(ArmReplay* r, int64_t info[3]) {
   unsigned long long c[3];
   RCU(cudaMemcpy(c, r->d.counters, sizeof(c), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 3; ++i) info[i] = (int64_t)c[i];
+  return ARMSIM_OK;
+}
+
+/* checkpointing: the whole ring + table + cursors as one opaque blob (valid for an identical ArmReplayConfig) */
+int64_t armsim_replay_state_bytes(ArmReplay* r) { return r ? (int64_t)r->bytes : (int64_t)ARMSIM_E_INVALID; }
+
+int armsim_replay_get_state(ArmReplay* r, void* host_dst, int64_t bytes) {
+  if (!r || !host_dst || bytes != (int64_t)r->bytes) return rfail(ARMSIM_E_STATE, "armsim_replay_get_state: need exactly %zu bytes", r ? r->bytes : (size_t)0);
+  RCU(cudaSetDevice(r->device));
+  RCU(cudaDeviceSynchronize());
+  RCU(cudaMemcpy(host_dst, r->block, r->bytes, cudaMemcpyDeviceToHost));
+  return ARMSIM_OK;
+}
+
+int armsim_replay_set_state(ArmReplay* r, const void* host_src, int64_t bytes) {
+  if (!r || !host_src || bytes != (int64_t)r->bytes) return rfail(ARMSIM_E_STATE, "armsim_replay_set_state: need exactly %zu bytes", r ? r->bytes : (size_t)0);
+  RCU(cudaSetDevice(r->device));
+  RCU(cudaDeviceSynchronize());
+  RCU(cudaMemcpy(r->block, host_src, r->bytes, cudaMemcpyHostToDevice));
   return ARMSIM_OK;
 }
 

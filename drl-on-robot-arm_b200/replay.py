@@ -115,6 +115,17 @@ class TrajectoryReplay:
         """number of committed trajectories still addressable (rl_utils.py:115); synchronises"""
         return min(self.info()["trajectories"], self.cfg.table_cap)
 
+    def state_blob(self):
+        """the whole replay (ring, trajectory table, cursors) as a uint8 array, for checkpoints"""
+        nb = int(L.lib().armsim_replay_state_bytes(self.h))
+        buf = np.empty(nb, np.uint8)
+        L.check_replay(L.lib().armsim_replay_get_state(self.h, buf.ctypes.data, nb))
+        return buf
+
+    def load_state_blob(self, buf):
+        buf = np.ascontiguousarray(buf, np.uint8)
+        L.check_replay(L.lib().armsim_replay_set_state(self.h, buf.ctypes.data, buf.nbytes))
+
     def table(self, count=None):
         count = self.size() if count is None else int(count)
         env, start, ln = np.zeros(count, np.int32), np.zeros(count, np.int64), np.zeros(count, np.int32)

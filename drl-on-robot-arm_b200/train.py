@@ -1,0 +1,237 @@
+"""VectorTrainer -- the reference's training loops (main.py:77-162 `run`, :165-231 `train_reach_with_TD3`, :449-584
+push / pick) re-expressed for N_envs lockstep environments on one GPU (or one shard per GPU).
+
+Reference, per episode of ONE env                         here, per lockstep step of N envs
+--------------------------------------------------------  ---------------------------------------------------------
+action = agent.take_action(state) + N(0, sigma)  :196-200  actions = agent.act(obs) + N(0, sigma)          (device)
+state, reward, done, ok = env.step(action)        :201      env.step(actions, final_obs=True)      (ONE kernel launch)
+traj.store_step(...); buffer.add_trajectory(traj) :205-206  replay.store(...)  (an env's done commits its trajectory)
+if buffer.size() >= minimal_episodes:             :209      the same gate, on committed trajectories
+    n_train x agent.train(buffer.sample(B, her))  :210-212  n_train updates per N finished episodes (one "episode-time")
+every 25 episodes: success_rate; if >= best:      :222-229  every 25 * N finished episodes: the same bookkeeping --
+    agent.save(prefix); her_ratio *= 0.75                    save-on-best, her_ratio decay x0.75
+
+The rollout step {actor forward, exploration noise, fused env step, replay store, episode statistics} is captured in
+ONE CUDA graph; statistics stay on the device and are read back every `sync_every` steps (one small copy).
+Multi-GPU: one process per GPU, each with its env + replay shard; the agents are replicas kept identical by the flat
+gradient all-reduce inside agent.train (distributed.GradBucket); logged statistics are summed over ranks.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .config import opt
+from .distributed import allreduce_scalars
+from .metrics import MetricsSink
+
+
+class VectorTrainer:
+    def __init__(self, env, agent, replay, noise_std=None, clip_actions=False, batch_size=None, n_train=None,
+                 minimal_episodes=None, use_her=True, her_ratio=None, dis_threshold=0.1, window_episodes=None, avg_window=10,
+                 sync_every=16, metrics=None, save_prefix=None, use_cuda_graph=True, max_updates_per_sync=None):
+        self.env, self.agent, self.replay = env, agent, replay
+        self.device = env.device
+        self.n = env.n
+        self.action_bound = float(agent.action_bound)
+        # main.py:200 adds N(0, 1 * opt.gamma) (the DISCOUNT doubles as the noise scale -- reference quirk, kept as default)
+        self.noise_std = float(opt.gamma if noise_std is None else noise_std)
+        self.clip_actions = bool(clip_actions)                  # run() clips to +-action_bound (main.py:116-117)
+        self.batch_size = int(batch_size or opt.batch_size)
+        self.n_train = int(n_train or opt.n_train)
+        self.minimal_episodes = int(opt.minimal_episodes if minimal_episodes is None else minimal_episodes)
+        self.use_her = bool(use_her)
+        self.her_ratio = float(opt.her_ratio if her_ratio is None else her_ratio)
+        self.dis_threshold = float(dis_threshold)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.window_episodes = int(window_episodes or 25 * self.n * self.world)      # main.py:222 `% 25`, per env
+        self.avg_window = int(avg_window)
+        self.sync_every = int(sync_every)
+        self.metrics = metrics if metrics is not None else MetricsSink()
+        self.save_prefix = save_prefix
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self.max_updates_per_sync = max_updates_per_sync
+        dev = self.device
+        # device-side episode statistics: [episodes finished, successes, sum of finished returns]
+        self.stats = torch.zeros(3, device=dev, dtype=torch.float64)
+        self.ep_return = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.actions = torch.zeros((self.n, env.act_dim), device=dev)
+        self.obs = None
+        self._graph = None
+        self._stream = torch.cuda.Stream(device=dev)
+        # host-side bookkeeping
+        self.steps = 0
+        self.updates = 0
+        self.episodes_seen = 0.0          # global (all ranks), as of the last sync
+        self.update_credit = 0.0
+        self.window_acc = np.zeros(3)     # episodes, successes, return sum of the open success-rate window
+        self.best_rate = 0.0
+        self.returns_log = []
+        self._last_stats = np.zeros(3)
+
+    # ------------------------------------------------------------------ rollout
+    def reset(self):
+        with torch.cuda.stream(self._stream):
+            self.obs = self.env.reset()
+            self.replay.begin(self.obs)
+            self.ep_return.zero_()
+        self._stream.synchronize()
+
+    def _rollout_body(self):
+        env = self.env
+        a = self.agent.act(env.obs)
+        a = a + torch.randn_like(a) * self.noise_std                              # main.py:200
+        if self.clip_actions:
+            a = a.clamp(-self.action_bound, self.action_bound)                    # main.py:117
+        self.actions.copy_(a)
+        obs, rew, done, succ = env.step(self.actions, final_obs=True)
+        self.replay.store(self.actions, rew, done, env.final_obs, obs)
+        self.ep_return += rew
+        d = done.to(torch.float32)
+        fin = torch.stack([d.sum(), succ.to(torch.float32).sum(), (self.ep_return * d).sum()]).to(torch.float64)
+        self.stats += fin
+        self.ep_return *= (1.0 - d)
+
+    def rollout_step(self):
+        """one lockstep step of all envs (one CUDA-graph replay once captured)"""
+        if self.obs is None:
+            self.reset()
+        with torch.cuda.stream(self._stream):
+            if not self.use_cuda_graph:
+                self._rollout_body()
+            elif self._graph is None:
+                for _ in range(3):                                                # warm-up outside capture (these steps count)
+                    self._rollout_body()
+                    self.steps += 1
+                self._stream.synchronize()
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph, stream=self._stream):
+                    self._rollout_body()
+                self._graph.replay()                                              # capture does not execute: run it once
+            else:
+                self._graph.replay()
+        self.steps += 1
+
+    # ------------------------------------------------------------------ learning
+    def train_updates(self, k):
+        with torch.cuda.stream(self._stream):
+            for _ in range(k):
+                batch = self.replay.sample(self.batch_size, self.use_her, self.dis_threshold, self.her_ratio)
+                self.agent.train(batch, sync=False)
+        self.updates += k
+
+    def _sync(self):
+        """read the device statistics, all-reduce them over ranks, run the updates that became due, log windows"""
+        self._stream.synchronize()
+        local = self.stats.cpu().numpy()
+        delta = local - self._last_stats
+        self._last_stats = local
+        if self.world > 1:
+            g = allreduce_scalars({"e": delta[0], "s": delta[1], "r": delta[2]})
+            delta = np.array([g["e"], g["s"], g["r"]])
+        self.episodes_seen += delta[0]
+        self.window_acc += delta
+        if delta[0] > 0:
+            mean_ret = delta[2] / delta[0]
+            self.returns_log.append(mean_ret)
+            self.metrics.plot("return", mean_ret, x=self.episodes_seen)                               # main.py:207
+            self.metrics.plot("avg_return", float(np.mean(self.returns_log[-self.avg_window:])), x=self.episodes_seen)  # :220
+        # n_train updates per N finished episodes, once minimal_episodes trajectories exist (main.py:209-212)
+        if self.episodes_seen >= self.minimal_episodes:
+            self.update_credit += delta[0] / float(self.n * self.world)
+            k = int(self.update_credit * self.n_train)
+            if self.max_updates_per_sync is not None:
+                k = min(k, int(self.max_updates_per_sync))
+            if k > 0:
+                self.update_credit -= k / float(self.n_train)
+                self.train_updates(k)
+        if self.window_acc[0] >= self.window_episodes:                                               # main.py:222-229
+            rate = self.window_acc[1] / self.window_acc[0]
+            self.metrics.plot("success_rate", rate, x=self.episodes_seen)
+            if rate >= self.best_rate:
+                if self.save_prefix and self.rank == 0:
+                    os.makedirs(os.path.dirname(os.path.abspath(self.save_prefix)), exist_ok=True)
+                    self.agent.save("%s%s" % (self.save_prefix, rate))
+                self.best_rate = rate
+                self.her_ratio *= 0.75
+            self.window_acc[:] = 0.0
+
+    def run(self, total_steps):
+        """advance every env by total_steps lockstep steps, learning as the reference's cadence dictates"""
+        end = self.steps + int(total_steps)
+        while self.steps < end:
+            self.rollout_step()
+            if self.steps % self.sync_every == 0 or self.steps >= end:
+                self._sync()
+        return {"steps": self.steps, "env_steps": self.steps * self.n * self.world, "updates": self.updates,
+                "episodes": self.episodes_seen, "success_rate": self.metrics.last("success_rate"),
+                "avg_return": self.metrics.last("avg_return"), "her_ratio": self.her_ratio}
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self, include_replay=True):
+        from . import _lib as L
+        env_state = {f: self.env.get_state(f) for f in range(L.F_IK_ITERS)}
+        self._stream.synchronize()
+        return {"agent": self.agent.state_dict(), "env": env_state, "env_obs": self.env.obs.cpu(),
+                "replay": self.replay.state_blob() if include_replay else None,
+                "stats": self.stats.cpu(), "ep_return": self.ep_return.cpu(),
+                "host": {k: getattr(self, k) for k in ("steps", "updates", "episodes_seen", "update_credit", "best_rate", "her_ratio")},
+                "window_acc": self.window_acc.copy(), "last_stats": self._last_stats.copy(), "returns_log": list(self.returns_log),
+                "torch_rng": torch.get_rng_state(), "cuda_rng": torch.cuda.get_rng_state(self.device)}
+
+    def load_state_dict(self, sd):
+        self.agent.load_state_dict(sd["agent"])
+        for f, v in sd["env"].items():
+            self.env.set_state(f, v)
+        self.env.obs.copy_(sd["env_obs"].to(self.device))
+        self.obs = self.env.obs
+        if sd["replay"] is not None:
+            self.replay.load_state_blob(sd["replay"])
+        self.stats.copy_(sd["stats"].to(self.device))
+        self.ep_return.copy_(sd["ep_return"].to(self.device))
+        for k, v in sd["host"].items():
+            setattr(self, k, v)
+        self.window_acc, self._last_stats = sd["window_acc"].copy(), sd["last_stats"].copy()
+        self.returns_log = list(sd["returns_log"])
+        torch.set_rng_state(sd["torch_rng"])
+        torch.cuda.set_rng_state(sd["cuda_rng"], self.device)
+
+
+def save_checkpoint(path, trainer, include_replay=True):
+    """everything needed to resume a run (the reference only ever saves actor/critic weights, TD3_mlp.py:163-168)"""
+    tmp = path + ".tmp"
+    torch.save(trainer.state_dict(include_replay), tmp)
+    os.replace(tmp, path)
+
+
+def load_checkpoint(path, trainer):
+    trainer.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
+
+
+TASK_DEFAULTS = {   # state_dim, action_bound (main.py:87 high[0]+0.3 for reach; :457 / :526 0.4 for push / pick), replay kind
+    "reach": (6, 0.7, "reach"), "push": (9, 0.4, "push"), "pick": (9, 0.4, "push"),
+}
+
+
+def make_trainer(task="reach", algo="TD3_MLP", n_envs=4096, device=None, seed=None, window=1024, distributed=None, **kw):
+    """getattr(envs, opt.env) / getattr(algo, opt.algo) of main.py:83,95 for the batched engine"""
+    from . import algo as A
+    from .distributed import make_sharded_env
+    from .replay import TrajectoryReplay
+    seed = opt.random_seed if seed is None else seed
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    distributed = (world > 1) if distributed is None else distributed
+    state_dim, bound, kind = TASK_DEFAULTS[task]
+    torch.manual_seed(seed)                                                       # main.py:175-177 (same init on every rank)
+    env = make_sharded_env(task, n_envs * world, rank=rank, world=world, device=device, seed=seed, auto_reset=True)
+    agent = getattr(A, algo)(state_dim=state_dim, action_dim=3, action_bound=bound, device=env.device, distributed=distributed)
+    if distributed:
+        agent.broadcast_parameters(0)
+    torch.manual_seed(seed + 1000 * (rank + 1))                                   # exploration noise differs per rank
+    replay = TrajectoryReplay(n_envs=env.n, obs_dim=env.obs_dim, act_dim=3, window=window, kind=kind, device=env.device,
+                              seed=seed + rank)
+    return VectorTrainer(env, agent, replay, **kw)

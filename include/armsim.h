@@ -220,6 +220,11 @@ int armsim_replay_gather(ArmReplay* rep, int32_t batch, const int32_t* slot_dev,
  * the first `count` trajectory-table entries (env, absolute start row, length). */
 int armsim_replay_info(ArmReplay* rep, int64_t info[3]);
 int armsim_replay_table(ArmReplay* rep, int32_t* env_host, int64_t* start_host, int32_t* len_host, int32_t count);
+/* Checkpoint / resume: the ring, the trajectory table and every cursor as one opaque blob (only valid for a replay
+ * created with the identical ArmReplayConfig).  Synchronous. */
+int64_t armsim_replay_state_bytes(ArmReplay* rep);
+int armsim_replay_get_state(ArmReplay* rep, void* host_dst, int64_t bytes);
+int armsim_replay_set_state(ArmReplay* rep, const void* host_src, int64_t bytes);
 const char* armsim_replay_last_error(void);
 
 #ifdef __cplusplus
