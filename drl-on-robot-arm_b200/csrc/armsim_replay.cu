@@ -57,10 +57,15 @@ struct ArmReplay {
 
 constexpr int RB = 256;
 
-// one lockstep row: copies + trajectory bookkeeping; the LAST block to finish advances the absolute step counter
+// one lockstep row: five coalesced copies by the whole grid; the LAST block to finish then commits the trajectories of
+// the envs that terminated in this row IN ENV ORDER (block-wide prefix sum over the done flags -- deterministic table
+// slots, so a resumed run samples the same transitions) and advances the absolute step counter.
 __global__ void __launch_bounds__(RB)
 replay_store_kernel(const ReplayDev D, const float* __restrict__ action, const float* __restrict__ reward,
                     const uint8_t* __restrict__ done, const float* __restrict__ final_obs, const float* __restrict__ obs_out) {
+  __shared__ unsigned int s_warp[RB / 32];
+  __shared__ unsigned int s_running;
+  __shared__ bool s_last;
   const unsigned long long now = D.counters[0];
   const size_t row = (size_t)(now % (unsigned long long)D.W);
   const int n = D.n;
@@ -72,23 +77,52 @@ replay_store_kernel(const ReplayDev D, const float* __restrict__ action, const f
   for (int i = tid; i < n * D.A; i += nth) ac[i] = action[i];
   for (int e = tid; e < n; e += nth) {
     D.rew[row * n + e] = reward[e];
-    const uint8_t dn = done[e];
-    D.done[row * n + e] = dn;
-    if (dn) {
-      const long long s = D.ep_start[e];
-      const long long L = (long long)now - s + 1;
-      if (L >= 1 && L < (long long)D.W) {        // an episode longer than the ring cannot be replayed
-        const unsigned long long slot = atomicAdd(&D.counters[1], 1ull) % (unsigned long long)D.cap;
-        D.t_env[slot] = e;
-        D.t_start[slot] = s;
-        D.t_len[slot] = (int)L;
-      }
-      D.ep_start[e] = (long long)now + 1;
-    }
+    D.done[row * n + e] = done[e];
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(D.blocks_done, 1u) == gridDim.x - 1) {
+  if (threadIdx.x == 0) s_last = atomicAdd(D.blocks_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) s_running = 0;
+  const unsigned long long base = D.counters[1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < n; c0 += RB) {
+    const int e = c0 + threadIdx.x;
+    long long s = 0, L = 0;
+    bool commit = false, dn = false;
+    if (e < n) {
+      dn = done[e] != 0;
+      if (dn) {
+        s = D.ep_start[e];
+        L = (long long)now - s + 1;
+        commit = L >= 1 && L < (long long)D.W;       // an episode longer than the ring cannot be replayed
+      }
+    }
+    const unsigned int bal = __ballot_sync(0xffffffffu, commit);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    unsigned int before = __popc(bal & ((1u << lane) - 1u)), total = 0;
+    for (int w = 0; w < RB / 32; ++w) {
+      const unsigned int c = s_warp[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    const unsigned int run = s_running;
+    if (commit) {
+      const unsigned long long slot = (base + run + before) % (unsigned long long)D.cap;
+      D.t_env[slot] = e;
+      D.t_start[slot] = s;
+      D.t_len[slot] = (int)L;
+    }
+    if (dn) D.ep_start[e] = (long long)now + 1;
+    __syncthreads();
+    if (threadIdx.x == 0) s_running = run + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    D.counters[1] = base + s_running;
     *D.blocks_done = 0;
     __threadfence();
     D.counters[0] = now + 1;
