@@ -43,10 +43,13 @@ struct ArmSim {
   char* h_pin = nullptr;         // mapped + portable pinned block: [actions | obs | reward | done | success | flag]
   char* d_io = nullptr;          // device twin of the same layout (large batches: DMA copies instead of zero-copy)
   size_t off_obs = 0, off_reward = 0, off_done = 0, off_success = 0, out_bytes = 0, act_bytes = 0;
-  unsigned int* d_counter = nullptr;   // blocks-finished counter of the doorbell
-  volatile unsigned int* h_flag = nullptr;
-  unsigned int seq = 0;
+  unsigned int* d_cta_seq = nullptr;   // per-block launch counters of the doorbells (device)
+  volatile unsigned int* h_flags = nullptr;   // per-block doorbells (mapped host memory, tail of h_pin)
+  unsigned int seq = 0;                // host-path launches so far == the value every doorbell shows when one is done
+  int grid = 0;
   bool zero_copy = true;
+  cudaGraphExec_t host_graph = nullptr;   // the zero-copy host step as an instantiated graph (parameters never change)
+  bool host_graph_tried = false;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
 };
@@ -208,7 +211,8 @@ void armsim_destroy(ArmSim* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->state_block) cudaFree(s->state_block);
   if (s->d_io) cudaFree(s->d_io);
-  if (s->d_counter) cudaFree(s->d_counter);
+  if (s->host_graph) cudaGraphExecDestroy(s->host_graph);
+  if (s->d_cta_seq) cudaFree(s->d_cta_seq);
   if (s->h_pin) cudaFreeHost(s->h_pin);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -232,16 +236,16 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
 // the parameter-driven one
 #define ARMSIM_STEP_CASE(TASK, ROBOT)                                                                           \
   case (TASK) * 4 + (ROBOT):                                                                                    \
-    launch_k(step_lane_kernel<TASK, ROBOT>, grid, st, H.flag == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+    launch_k(step_lane_kernel<TASK, ROBOT>, grid, st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     break;
 
 #define ARMSIM_TORQUE_CASE(TASK, ROBOT)                                                                                \
   case (TASK) * 4 + (ROBOT):                                                                                           \
-    launch_k(step_torque_kernel<TASK, ROBOT>, grid, st, H.flag == nullptr, s->chain, s->task, s->dyn, s->S, a, o, r, d, su, fo, H); \
+    launch_k(step_torque_kernel<TASK, ROBOT>, grid, st, H.flags == nullptr, s->chain, s->task, s->dyn, s->S, a, o, r, d, su, fo, H); \
     break;
 
 static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st,
-                       const HostNotify H = HostNotify{nullptr, nullptr, 0u}, float* fo = nullptr) {
+                       const HostNotify H = HostNotify{nullptr, nullptr}, float* fo = nullptr) {
   const int grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
   if (s->cfg.mode == ARMSIM_MODE_TORQUE) {
     switch (s->cfg.task * 4 + s->cfg.robot) {
@@ -371,17 +375,19 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   // zero-copy (kernel reads actions from / writes results to mapped host memory, completion by doorbell) while the
   // per-step payload is small enough for PCIe latency, not bandwidth, to dominate; DMA copies beyond that
   s->zero_copy = n <= 65536;
+  s->grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
+  const size_t flag_bytes = pad((size_t)s->grid * sizeof(unsigned int));
   if (cudaMalloc((void**)&s->d_io, s->act_bytes + s->out_bytes) != cudaSuccess ||
-      cudaMalloc((void**)&s->d_counter, sizeof(unsigned int)) != cudaSuccess ||
-      cudaMemset(s->d_counter, 0, sizeof(unsigned int)) != cudaSuccess ||
-      cudaHostAlloc((void**)&s->h_pin, s->act_bytes + s->out_bytes + 256, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+      cudaMalloc((void**)&s->d_cta_seq, flag_bytes) != cudaSuccess ||
+      cudaMemset(s->d_cta_seq, 0, flag_bytes) != cudaSuccess ||
+      cudaHostAlloc((void**)&s->h_pin, s->act_bytes + s->out_bytes + flag_bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
       cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     armsim_destroy(s);
     return fail(ARMSIM_E_NOMEM, "armsim_create: staging allocation failed");
   }
-  s->h_flag = (volatile unsigned int*)(s->h_pin + s->act_bytes + s->out_bytes);
-  *s->h_flag = 0;
+  s->h_flags = (volatile unsigned int*)(s->h_pin + s->act_bytes + s->out_bytes);
+  memset((void*)s->h_flags, 0, flag_bytes);
   int rc = launch_reset(s, nullptr, nullptr, s->stream);
   if (rc == ARMSIM_OK && cudaStreamSynchronize(s->stream) != cudaSuccess) rc = fail(ARMSIM_E_CUDA, "armsim_create: initial reset failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (rc != ARMSIM_OK) { armsim_destroy(s); return rc; }
@@ -401,17 +407,24 @@ int armsim_step(ArmSim* s, const float* action_dev, float* obs_dev, float* rewar
   return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream);
 }
 
-// Wait for the kernel's doorbell.  Polls the mapped flag; every so often asks the driver whether the stream died so
-// a faulting kernel turns into an error code instead of a hang.
-static int wait_doorbell(ArmSim* s, unsigned int seq) {
+// Wait until every block's doorbell shows `seq`.  Polls the mapped words; every so often asks the driver whether the
+// stream died so a faulting kernel turns into an error code instead of a hang.
+static int wait_doorbells(ArmSim* s, unsigned int seq) {
+  const volatile unsigned int* f = s->h_flags;
+  const int grid = s->grid;
+  int b = 0;                                   // doorbells [0, b) already seen at seq
   for (unsigned long long spins = 1;; ++spins) {
-    if (*s->h_flag == seq) return ARMSIM_OK;
+    while (b < grid && f[b] == seq) ++b;
+    if (b == grid) return ARMSIM_OK;
 #if defined(__x86_64__) || defined(__i386__)
     __builtin_ia32_pause();
 #endif
     if ((spins & 0xFFFFull) == 0) {
       cudaError_t q = cudaStreamQuery(s->stream);
-      if (q == cudaSuccess) return *s->h_flag == seq ? ARMSIM_OK : fail(ARMSIM_E_CUDA, "armsim_step_host: kernel finished without ringing the doorbell");
+      if (q == cudaSuccess) {
+        while (b < grid && f[b] == seq) ++b;
+        return b == grid ? ARMSIM_OK : fail(ARMSIM_E_CUDA, "armsim_step_host: kernel finished without ringing every doorbell");
+      }
       if (q != cudaErrorNotReady) return fail(ARMSIM_E_CUDA, "armsim_step_host: %s", cudaGetErrorString(q));
     }
   }
@@ -432,7 +445,7 @@ int armsim_step_ex(ArmSim* s, const float* action_dev, float* obs_dev, float* re
                    float* final_obs_dev, void* stream) {
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_ex: null handle");
   if (!action_dev || !obs_dev || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_step_ex: null buffer");
-  return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream, HostNotify{nullptr, nullptr, 0u},
+  return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream, HostNotify{nullptr, nullptr},
                      final_obs_dev);
 }
 
@@ -447,12 +460,36 @@ int armsim_step_host(ArmSim* s, const float* action_host, float* obs_host, float
   // callers that work in the handle's own pinned block (armsim_host_buffers) skip the staging memcpys
   if ((const char*)action_host != s->h_pin) memcpy(s->h_pin, action_host, n * s->act_dim * 4);
   if (s->zero_copy) {
-    const unsigned int seq = ++s->seq ? s->seq : ++s->seq;   // never 0 (the flag's idle value)
-    HostNotify H{s->d_counter, (unsigned int*)s->h_flag, seq};
-    int rc = launch_step(s, (const float*)s->h_pin, (float*)(h_out + s->off_obs), (float*)(h_out + s->off_reward),
-                         (uint8_t*)(h_out + s->off_done), (uint8_t*)(h_out + s->off_success), s->stream, H);
+    const unsigned int seq = ++s->seq;
+    HostNotify H{s->d_cta_seq, (unsigned int*)s->h_flags};
+    float* o = (float*)(h_out + s->off_obs);
+    float* r = (float*)(h_out + s->off_reward);
+    uint8_t *d = (uint8_t*)(h_out + s->off_done), *su = (uint8_t*)(h_out + s->off_success);
+    if (!s->host_graph_tried) {   // first call: record the launch once; its parameters are the same for every later step
+      s->host_graph_tried = true;
+      cudaGraph_t g = nullptr;
+      if (getenv("ARMSIM_HOST_GRAPH") == nullptr || getenv("ARMSIM_HOST_GRAPH")[0] != '0') {
+        const int64_t launches0 = s->launches;
+        if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+          const int rc0 = launch_step(s, (const float*)s->h_pin, o, r, d, su, s->stream, H);
+          if (cudaStreamEndCapture(s->stream, &g) != cudaSuccess || rc0 != ARMSIM_OK ||
+              cudaGraphInstantiate(&s->host_graph, g, 0) != cudaSuccess)
+            s->host_graph = nullptr;
+          if (g) cudaGraphDestroy(g);
+        }
+        s->launches = launches0;
+        cudaGetLastError();
+      }
+    }
+    int rc = ARMSIM_OK;
+    if (s->host_graph) {
+      CU(cudaGraphLaunch(s->host_graph, s->stream));
+      s->launches += 1;
+    } else {
+      rc = launch_step(s, (const float*)s->h_pin, o, r, d, su, s->stream, H);
+    }
     if (rc) return rc;
-    rc = wait_doorbell(s, seq);
+    rc = wait_doorbells(s, seq);
     if (rc) return rc;
   } else {
     CU(cudaMemcpyAsync(s->d_io, s->h_pin, n * s->act_dim * 4, cudaMemcpyHostToDevice, s->stream));

@@ -106,7 +106,7 @@ __device__ __forceinline__ void reset_env(const ChainParams& C, const TaskParams
   for (int i = 0; i < 9; ++i) R[i] = T.init_R[i];
   if constexpr (TaskTraits<TASK>::HAS_CUBE) {
     S.grip[e] = 0.f;
-    cube::step(cb, p, R, TASK == ARMSIM_TASK_PICK, 0.f);   // p.stepSimulation() rl_push_env.py:242
+    cube::step<TASK == ARMSIM_TASK_PICK>(cb, p, R, 0.f);   // p.stepSimulation() rl_push_env.py:242
     const float d0 = cb.pos[0] - goal[0], d1 = cb.pos[1] - goal[1], d2 = cb.pos[2] - goal[2];
     S.last_dist[e] = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
     store_cube(S, n, e, cb);
@@ -180,7 +180,7 @@ __device__ __forceinline__ bool task_epilogue(const ChainParams& C, const TaskPa
   } else {
     constexpr bool PICK = TASK == ARMSIM_TASK_PICK;
     float grip = E.grip;
-    cube::step(cb, p, R, PICK, grip);                             // p.stepSimulation() rl_push_env.py:349
+    cube::step<PICK>(cb, p, R, grip);                             // p.stepSimulation() rl_push_env.py:349
     if constexpr (PICK) {
       if (grip < 0.5f && cube::gripper_distance(cb, p, R) < cube::CLOSE_DIST) {   // rl_pick_env.py:412-416
         const float h0 = cb.pos[0] - (p[0] + cube::GRIPPER_LEN * R[2]);
@@ -188,7 +188,7 @@ __device__ __forceinline__ bool task_epilogue(const ChainParams& C, const TaskPa
         const float h2 = cb.pos[2] - (p[2] + cube::GRIPPER_LEN * R[8]);
         grip = sqrtf(h0 * h0 + h1 * h1 + h2 * h2) < cube::HOLD_DIST ? 2.f : 1.f;
       }
-      cube::step(cb, p, R, PICK, grip);                           // second p.stepSimulation() :417
+      cube::step<PICK>(cb, p, R, grip);                           // second p.stepSimulation() :417
       if (live) S.grip[e] = grip;
     }
     const float d0 = cb.pos[0] - goal[0], d1 = cb.pos[1] - goal[1], d2 = cb.pos[2] - goal[2];
@@ -236,13 +236,16 @@ __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams&
   task_epilogue<TASK>(C, T, S, e, live, E, p, R, its, o, of, r, d, su);
 }
 
-// Completion doorbell of the host-buffer path (armsim_step_host): when `flag` is non-null the kernel's outputs go
-// straight to mapped pinned host memory and the LAST block to finish publishes `seq` there, so the host learns of
-// completion by polling one cache line instead of paying a stream synchronise.
+// Completion doorbells of the host-buffer path (armsim_step_host): when `flags` is non-null the kernel's outputs go
+// straight to mapped pinned host memory and EVERY block publishes its own sequence number there once its outputs are
+// out, so the host learns of completion by polling gridDim.x consecutive words instead of paying a stream
+// synchronise.  No device-wide atomic and one system-scope fence per block: the block barrier orders every thread's
+// output stores before thread 0's fence (PTX memory model: the fence is cumulative over what the barrier made
+// visible), and the fence orders them before the doorbell store.  The sequence number is a per-block counter in
+// device memory, so the launch parameters never change and the whole call replays from an instantiated CUDA graph.
 struct HostNotify {
-  unsigned int* counter;   // device: blocks finished (self-resetting)
-  unsigned int* flag;      // mapped host memory
-  unsigned int seq;
+  unsigned int* cta_seq;   // device: [gridDim.x] launches seen by each block
+  unsigned int* flags;     // mapped host memory: [gridDim.x]
 };
 
 // Programmatic dependent launch (see launch_k in armsim_capi.cu): nothing may be read from global memory before
@@ -251,16 +254,13 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ void notify_host(const HostNotify& H) {
-  if (H.flag == nullptr) return;
-  __threadfence_system();                 // this thread's output stores are visible to the host ...
-  __syncthreads();                        // ... for every thread of the block
+  if (H.flags == nullptr) return;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(H.counter, 1u) == gridDim.x - 1) {
-      *H.counter = 0;
-      __threadfence_system();
-      *(volatile unsigned int*)H.flag = H.seq;
-    }
+    const unsigned int seq = H.cta_seq[blockIdx.x] + 1u;
+    H.cta_seq[blockIdx.x] = seq;
+    __threadfence_system();
+    *(volatile unsigned int*)(H.flags + blockIdx.x) = seq;
   }
 }
 

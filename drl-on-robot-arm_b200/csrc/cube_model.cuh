@@ -32,6 +32,8 @@ struct State {
   float pos[3], quat[4], v[3], w[3];
 };
 
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 __device__ __forceinline__ void init(State& c, float x, float y, float z, float yaw) {
   c.pos[0] = x; c.pos[1] = y; c.pos[2] = z;
   float s, co;
@@ -144,25 +146,72 @@ __device__ __forceinline__ float gripper_distance(const State& cb, const float (
   return best;
 }
 
+// One projected-Gauss-Seidel row for a general direction (arm-proxy contacts).  rxd = r x dir and 1/k do not change
+// between sweeps but are recomputed (9 instructions) instead of held: registers are the scarcer resource here.
 __device__ __forceinline__ void row(State& cb, const float (&r)[3], const float (&dir)[3], float target, float lo, float hi,
                                     float& acc) {
   const float rxd[3] = {r[1] * dir[2] - r[2] * dir[1], r[2] * dir[0] - r[0] * dir[2], r[0] * dir[1] - r[1] * dir[0]};
   const float vrel = dir[0] * cb.v[0] + dir[1] * cb.v[1] + dir[2] * cb.v[2] + rxd[0] * cb.w[0] + rxd[1] * cb.w[1] + rxd[2] * cb.w[2];
-  const float k = INV_MASS + (rxd[0] * rxd[0] + rxd[1] * rxd[1] + rxd[2] * rxd[2]) * INV_INERTIA;
-  float dl = (target - vrel) / k;
-  float nl = fminf(fmaxf(acc + dl, lo), hi);
+  const float k = fmaf(rxd[0] * rxd[0] + rxd[1] * rxd[1] + rxd[2] * rxd[2], INV_INERTIA, INV_MASS);
+  float dl = (target - vrel) * rcp_approx(k);
+  const float nl = fminf(fmaxf(acc + dl, lo), hi);
   dl = nl - acc;
   acc = nl;
+  const float dli = dl * INV_INERTIA;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    cb.v[i] += dl * dir[i] * INV_MASS;
-    cb.w[i] += dl * rxd[i] * INV_INERTIA;
+    cb.v[i] = fmaf(dl, dir[i], cb.v[i]);      // INV_MASS = 1
+    cb.w[i] = fmaf(dli, rxd[i], cb.w[i]);
   }
 }
 
-// one p.stepSimulation() for the cube; grip: 0 open / push, 1 closed, 2 holding
-static __device__ __noinline__ void step(State& cb, const float (&ee)[3], const float (&Ree)[9], bool pick, float grip) {
-  if (pick && grip >= 1.5f) {
+// The three rows of a cube-corner / table contact.  The plane normal is +z, for which btPlaneSpace1 (tangents()) gives
+// t1 = (0,-1,0), t2 = (1,0,0); r x dir is then a signed permutation of r and the generic row collapses to a handful
+// of FMAs.  ik* = 1 / (1/m + |r x dir|^2 / I) per row, computed once per step.
+__device__ __forceinline__ void table_rows(State& cb, float r0, float r1, float r2, float bias, float ikn, float ik1, float ik2,
+                                           float& ln, float& l1, float& l2) {
+  const float r0i = r0 * INV_INERTIA, r1i = r1 * INV_INERTIA, r2i = r2 * INV_INERTIA;
+  {  // normal (0,0,1): r x n = (r1, -r0, 0)
+    const float vrel = fmaf(r1, cb.w[0], fmaf(-r0, cb.w[1], cb.v[2]));
+    const float nl = fminf(fmaxf(fmaf(bias - vrel, ikn, ln), 0.0f), 1e30f);
+    const float dl = nl - ln;
+    ln = nl;
+    cb.v[2] += dl;
+    cb.w[0] = fmaf(dl, r1i, cb.w[0]);
+    cb.w[1] = fmaf(-dl, r0i, cb.w[1]);
+  }
+  const float lim = MU * ln;
+  {  // t1 = (0,-1,0): r x t1 = (r2, 0, -r0)
+    const float vrel = fmaf(r2, cb.w[0], fmaf(-r0, cb.w[2], -cb.v[1]));
+    const float nl = fminf(fmaxf(fmaf(-vrel, ik1, l1), -lim), lim);
+    const float dl = nl - l1;
+    l1 = nl;
+    cb.v[1] -= dl;
+    cb.w[0] = fmaf(dl, r2i, cb.w[0]);
+    cb.w[2] = fmaf(-dl, r0i, cb.w[2]);
+  }
+  {  // t2 = (1,0,0): r x t2 = (0, r2, -r1)
+    const float vrel = fmaf(r2, cb.w[1], fmaf(-r1, cb.w[2], cb.v[0]));
+    const float nl = fminf(fmaxf(fmaf(-vrel, ik2, l2), -lim), lim);
+    const float dl = nl - l2;
+    l2 = nl;
+    cb.v[0] += dl;
+    cb.w[1] = fmaf(dl, r2i, cb.w[1]);
+    cb.w[2] = fmaf(-dl, r1i, cb.w[2]);
+  }
+}
+
+// one p.stepSimulation() for the cube; grip: 0 open / push, 1 closed, 2 holding.
+//
+// Same contact list and the same Gauss-Seidel order as oracle/cube_model.h (corners 0..7 in index order, then the arm
+// proxies), but every contact has a STATIC slot -- 8 corner slots + NP proxy slots with an "active" bit -- instead of
+// a compacted array: the slots are indexed by unrolled compile-time constants, so the whole contact set lives in
+// registers (the compacted, dynamically indexed array of round 1's first version lived in local memory: 1 KB stack
+// frame, ~170 instructions per contact per sweep; now ~45 for a corner).  The corner lever arm r is rebuilt from the
+// three half-edge vectors with sign flips (6 FADD) rather than held.
+template <bool PICK>
+static __device__ __noinline__ void step(State& cb, const float (&ee)[3], const float (&Ree)[9], float grip) {
+  if (PICK && grip >= 1.5f) {
     cb.pos[0] = ee[0] + GRIPPER_LEN * Ree[2];
     cb.pos[1] = ee[1] + GRIPPER_LEN * Ree[5];
     cb.pos[2] = ee[2] + GRIPPER_LEN * Ree[8];
@@ -176,53 +225,80 @@ static __device__ __noinline__ void step(State& cb, const float (&ee)[3], const 
 
   float R[9];
   rot(cb.quat, R);
-  Contact K[MAX_CONTACTS];
-  int nk = 0;
+  float H[9];                        // half-edge vectors: column k of R times HALF
+#pragma unroll
+  for (int i = 0; i < 9; ++i) H[i] = R[i] * HALF;
+
+  // ---- corner slots
+  unsigned active = 0u;
+  float tb[8], tln[8], tl1[8], tl2[8], tkn[8], tk1[8], tk2[8];
+#pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const float l0 = (c & 1) ? HALF : -HALF, l1 = (c & 2) ? HALF : -HALF, l2 = (c & 4) ? HALF : -HALF;
     float r[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) r[i] = R[3 * i] * l0 + R[3 * i + 1] * l1 + R[3 * i + 2] * l2;
+    for (int i = 0; i < 3; ++i)
+      r[i] = ((c & 1) ? H[3 * i] : -H[3 * i]) + ((c & 2) ? H[3 * i + 1] : -H[3 * i + 1]) + ((c & 4) ? H[3 * i + 2] : -H[3 * i + 2]);
     const float gap = cb.pos[2] + r[2] - TABLE_Z;
-    if (gap < MARGIN) {
-      Contact& k = K[nk++];
-      k.r[0] = r[0]; k.r[1] = r[1]; k.r[2] = r[2];
-      k.n[0] = 0.f; k.n[1] = 0.f; k.n[2] = 1.f;
-      k.bias = gap < 0.f ? -ERP * gap * INV_DT : -gap * INV_DT;
-      k.ln = k.l1 = k.l2 = 0.f;
-      tangents(k);
-    }
+    if (gap < MARGIN) active |= 1u << c;
+    tb[c] = gap < 0.f ? -ERP * gap * INV_DT : -gap * INV_DT;
+    tln[c] = tl1[c] = tl2[c] = 0.f;
+    const float a = r[0] * r[0], b = r[1] * r[1], d = r[2] * r[2];
+    tkn[c] = rcp_approx(fmaf(a + b, INV_INERTIA, INV_MASS));
+    tk1[c] = rcp_approx(fmaf(d + a, INV_INERTIA, INV_MASS));
+    tk2[c] = rcp_approx(fmaf(d + b, INV_INERTIA, INV_MASS));
   }
+
+  // ---- arm-proxy slots
+  constexpr int NP = PICK ? 3 : 1;
   float C[3][3], rad[3];
-  const int np = arm_proxies(ee, Ree, pick, grip, C, rad);
-  for (int p = 0; p < np; ++p) {
+  const int np = arm_proxies(ee, Ree, PICK, grip, C, rad);
+  Contact K[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
     float rr[3], nn[3];
     const float d = sphere_query(cb, R, C[p], rad[p], rr, nn);
-    if (d < 0.f) {
-      Contact& k = K[nk++];
+    if (p < np && d < 0.f) {
+      active |= 1u << (8 + p);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) { k.r[i] = rr[i]; k.n[i] = nn[i]; }
-      k.bias = -ERP * d * INV_DT;
-      k.ln = k.l1 = k.l2 = 0.f;
-      tangents(k);
+      for (int i = 0; i < 3; ++i) { K[p].r[i] = rr[i]; K[p].n[i] = nn[i]; }
+      K[p].bias = -ERP * d * INV_DT;
+      tangents(K[p]);
+    }
+    K[p].ln = K[p].l1 = K[p].l2 = 0.f;
+  }
+
+  if (active) {
+    for (int it = 0; it < PGS_ITERS; ++it) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (active & (1u << c)) {
+          const float r0 = ((c & 1) ? H[0] : -H[0]) + ((c & 2) ? H[1] : -H[1]) + ((c & 4) ? H[2] : -H[2]);
+          const float r1 = ((c & 1) ? H[3] : -H[3]) + ((c & 2) ? H[4] : -H[4]) + ((c & 4) ? H[5] : -H[5]);
+          const float r2 = ((c & 1) ? H[6] : -H[6]) + ((c & 2) ? H[7] : -H[7]) + ((c & 4) ? H[8] : -H[8]);
+          table_rows(cb, r0, r1, r2, tb[c], tkn[c], tk1[c], tk2[c], tln[c], tl1[c], tl2[c]);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        if (active & (1u << (8 + p))) {
+          Contact& k = K[p];
+          row(cb, k.r, k.n, k.bias, 0.0f, 1e30f, k.ln);
+          const float lim = MU * k.ln;
+          row(cb, k.r, k.t1, 0.0f, -lim, lim, k.l1);
+          row(cb, k.r, k.t2, 0.0f, -lim, lim, k.l2);
+        }
+      }
     }
   }
-  for (int it = 0; it < PGS_ITERS; ++it) {
-    for (int i = 0; i < nk; ++i) {
-      Contact& k = K[i];
-      row(cb, k.r, k.n, k.bias, 0.0f, 1e30f, k.ln);
-      const float lim = MU * k.ln;
-      row(cb, k.r, k.t1, 0.0f, -lim, lim, k.l1);
-      row(cb, k.r, k.t2, 0.0f, -lim, lim, k.l2);
-    }
-  }
 #pragma unroll
-  for (int i = 0; i < 3; ++i) cb.pos[i] += cb.v[i] * DT;
-  const float wn = sqrtf(cb.w[0] * cb.w[0] + cb.w[1] * cb.w[1] + cb.w[2] * cb.w[2]);
-  const float ang = wn * DT;
-  float s, co;
-  sincosf(0.5f * ang, &s, &co);
-  s = ang > 1e-6f ? s / wn : 0.5f * DT * (1.0f - ang * ang * (1.0f / 24.0f));
+  for (int i = 0; i < 3; ++i) cb.pos[i] = fmaf(cb.v[i], DT, cb.pos[i]);
+  // quaternion exponential map; half angle = |w| dt / 2 is far inside [-pi/4, pi/4] (|w| < 370 rad/s): polynomials only
+  const float w2 = cb.w[0] * cb.w[0] + cb.w[1] * cb.w[1] + cb.w[2] * cb.w[2];
+  const float h2 = w2 * (0.25f * DT * DT);                   // (half angle)^2
+  // sin(h)/|w| = (dt/2) sin(h)/h,  sin(h)/h = 1 - h2/6 + h2^2/120 - h2^3/5040 ;  cos(h) = 1 - h2/2 + h2^2/24 - ...
+  const float sinc = fmaf(h2, fmaf(h2, fmaf(h2, -1.9841270e-4f, 8.3333333e-3f), -1.6666667e-1f), 1.0f);
+  const float co = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
+  const float s = 0.5f * DT * sinc;
   const float dq[4] = {cb.w[0] * s, cb.w[1] * s, cb.w[2] * s, co};
   const float* q = cb.quat;
   float nq[4] = {dq[3] * q[0] + dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1],

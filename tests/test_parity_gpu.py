@@ -386,6 +386,33 @@ def test_pinned_host_buffers_are_copy_free_and_equal(pkg, torch_cuda):
         h1.close(); h2.close()
 
 
+def test_host_doorbells_never_publish_stale_results(pkg, torch_cuda):
+    """stress of the zero-copy host step (graph replay + per-block doorbells): 1500 back-to-back steps whose actions
+    change every step; every step's host-visible results must equal the device-pointer path's bit for bit -- a doorbell
+    that rang before a block's outputs landed would show the previous step's rows"""
+    torch = torch_cuda
+    n = 4096
+    rng = np.random.default_rng(4)
+    acts = rng.uniform(-0.7, 0.7, (16, n, 3)).astype(np.float32)
+    acts_d = torch.from_numpy(acts).cuda()
+    h = pkg.ArmSimHandle("reach", n_envs=n, seed=11, auto_reset=True)
+    e = pkg.BatchedArmEnv("reach", n_envs=n, seed=11, device="cuda:0", auto_reset=True)
+    act = h.host_buffers()[0]
+    bad = 0
+    for k in range(1500):
+        act[:] = acts[k % 16]
+        oh, rh, dh, sh = h.step_pinned()
+        od, rd, dd, sd = e.step(acts_d[k % 16])
+        if k % 50 == 0 or k > 1450:
+            bad += int(not (np.array_equal(oh, od.cpu().numpy()) and np.array_equal(rh, rd.cpu().numpy())
+                            and np.array_equal(dh, dd.cpu().numpy()) and np.array_equal(sh, sd.cpu().numpy())))
+        else:
+            bad += int(not np.array_equal(rh, rd.cpu().numpy()))
+    assert bad == 0
+    assert h.launch_count == 1 + 1500
+    h.close(); e.close()
+
+
 def test_host_path_large_batch_uses_dma_copies(pkg, torch_cuda):
     """n > 65536 takes the cudaMemcpyAsync route of armsim_step_host; same results as the device-pointer path"""
     torch = torch_cuda
