@@ -80,6 +80,45 @@ __global__ void __launch_bounds__(128) k_server(const float* __restrict__ in, fl
   }
 }
 
+// ping-pong only: ONE thread polls the host word and echoes it back (pure PCIe poll round trip)
+__global__ void k_pingpong(volatile unsigned* cmd, volatile unsigned* flag, int max_rounds) {
+  for (int round = 1; round <= max_rounds; ++round) {
+    const long long t0 = clock64();
+    while (*cmd < (unsigned)round) { if (clock64() - t0 > 4000000000ll) return; }
+    *flag = (unsigned)round;
+  }
+}
+
+// server v2: block 0 / thread 0 is the only poller of host memory; it relays the command through a device word that
+// the other blocks poll in L2.  Per-block doorbells back to the host.
+__global__ void __launch_bounds__(128) k_server2(const float* __restrict__ in, float* __restrict__ out, int nin, int nout, int spin,
+                                                 volatile unsigned* cmd, volatile unsigned* relay, unsigned* flags, int max_rounds) {
+  __shared__ int s_quit;
+  for (int round = 1; round <= max_rounds; ++round) {
+    if (threadIdx.x == 0) {
+      s_quit = 0;
+      const long long t0 = clock64();
+      if (blockIdx.x == 0) {
+        while (*cmd < (unsigned)round) { if (clock64() - t0 > 4000000000ll) { s_quit = 1; break; } }
+        *relay = s_quit ? 0xffffffffu : (unsigned)round;
+      } else {
+        unsigned v;
+        while ((v = *relay) < (unsigned)round) { if (clock64() - t0 > 6000000000ll) { s_quit = 1; break; } }
+        if (v == 0xffffffffu) s_quit = 1;
+      }
+    }
+    __syncthreads();
+    if (s_quit) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    float acc = 0.f;
+    for (int i = t; i < nin; i += nt) acc += __ldcv(in + i);
+    if (spin) { const long long t0 = clock64(); while (clock64() - t0 < spin) { } }
+    for (int i = t; i < nout; i += nt) out[i] = acc + (float)i;
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence_system(); *(volatile unsigned*)(flags + blockIdx.x) = (unsigned)round; }
+  }
+}
+
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int main(int argc, char** argv) {
@@ -178,6 +217,35 @@ int main(int argc, char** argv) {
     CK(cudaStreamSynchronize(st));
     std::sort(t.begin(), t.end());
     printf("%-64s median %6.2f us   p10 %6.2f   p90 %6.2f\n", "persistent server: host doorbell -> zero-copy step -> doorbell", 1e6 * t[reps / 2], 1e6 * t[reps / 10], 1e6 * t[reps * 9 / 10]);
+  }
+  {
+    volatile unsigned* vc = h_cmd; *vc = 0; *vf = 0;
+    const int rounds = reps + 50;
+    k_pingpong<<<1, 1, 0, st>>>(h_cmd, h_flag, rounds);
+    unsigned r = 0;
+    std::vector<double> t(reps);
+    for (int k = 0; k < 50; ++k) { *vc = ++r; __sync_synchronize(); wait(r); }
+    for (int k = 0; k < reps; ++k) { const double t0 = now(); *vc = ++r; __sync_synchronize(); wait(r); t[k] = now() - t0; }
+    CK(cudaStreamSynchronize(st));
+    std::sort(t.begin(), t.end());
+    printf("%-64s median %6.2f us   p10 %6.2f   p90 %6.2f\n", "ping-pong: host word -> 1 GPU thread -> host word", 1e6 * t[reps / 2], 1e6 * t[reps / 10], 1e6 * t[reps * 9 / 10]);
+  }
+  for (int variant = 0; variant < 2; ++variant) {
+    unsigned* h_flags; CK(cudaHostAlloc(&h_flags, 4096, cudaHostAllocMapped)); memset(h_flags, 0, 4096);
+    unsigned* d_relay; CK(cudaMalloc(&d_relay, 4)); CK(cudaMemset(d_relay, 0, 4));
+    volatile unsigned* vfl = h_flags;
+    auto waitall = [&](unsigned s) { for (;;) { bool ok = true; for (int b = 0; b < grid; ++b) ok &= (vfl[b] == s); if (ok) break; __builtin_ia32_pause(); } };
+    volatile unsigned* vc = h_cmd; *vc = 0;
+    const int rounds = reps + 50;
+    const int sp = variant ? spin : 0;
+    k_server2<<<grid, 128, 0, st>>>(h_in, h_out, variant ? nin : 0, variant ? nout : 0, sp, h_cmd, d_relay, h_flags, rounds);
+    unsigned r = 0;
+    std::vector<double> t(reps);
+    for (int k = 0; k < 50; ++k) { *vc = ++r; __sync_synchronize(); waitall(r); }
+    for (int k = 0; k < reps; ++k) { const double t0 = now(); *vc = ++r; __sync_synchronize(); waitall(r); t[k] = now() - t0; }
+    CK(cudaStreamSynchronize(st));
+    std::sort(t.begin(), t.end());
+    printf("%-64s median %6.2f us   p10 %6.2f   p90 %6.2f\n", variant ? "server v2 (1 poller + relay): zero-copy step" : "server v2 (1 poller + relay): empty step", 1e6 * t[reps / 2], 1e6 * t[reps / 10], 1e6 * t[reps * 9 / 10]);
   }
   printf("done\n");
   return 0;

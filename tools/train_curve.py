@@ -1,0 +1,45 @@
+"""python tools/train_curve.py [task] [algo] [n_envs] [episode_times] [out.json]
+The reference's `train_reach_with_TD3` loop (main.py:165-231) on the batched engine: N envs in lockstep, the reference's
+update cadence (n_train updates per episode-time), HER, save-on-best bookkeeping.  Prints / stores the success-rate
+series (one point per 25 episode-times, main.py:222) next to the reference's learning-curve pins."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import drl_on_robot_arm_b200 as pkg  # noqa: F401
+from drl_on_robot_arm_b200 import metrics, train
+
+task = sys.argv[1] if len(sys.argv) > 1 else "reach"
+algo = sys.argv[2] if len(sys.argv) > 2 else "TD3_MLP"
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+episode_times = int(sys.argv[4]) if len(sys.argv) > 4 else 100
+out = sys.argv[5] if len(sys.argv) > 5 else None
+budget_s = float(os.environ.get("TRAIN_BUDGET_S", "600"))
+
+sink = metrics.MetricsSink()
+tr = train.make_trainer(task=task, algo=algo, n_envs=n, device="cuda:0", seed=0, window=1024, metrics=sink, sync_every=32,
+                        window_episodes=5 * n, clip_actions=(os.environ.get("CLIP", "0") == "1"),
+                        noise_std=float(os.environ["NOISE"]) if "NOISE" in os.environ else None)
+t0 = time.time()
+chunk = 501
+log = []
+for k in range(episode_times):
+    res = tr.run(chunk)
+    torch.cuda.synchronize()
+    el = time.time() - t0
+    log.append({"episode_time": k + 1, "wall_s": el, "env_steps": res["env_steps"], "updates": res["updates"],
+                "success_rate": res["success_rate"], "avg_return": res["avg_return"], "her_ratio": res["her_ratio"]})
+    if (k + 1) % 5 == 0 or k == 0:
+        print(json.dumps(log[-1]), flush=True)
+    if el > budget_s:
+        break
+summary = {"task": task, "algo": algo, "n_envs": n, "episode_times": len(log), "wall_s": time.time() - t0,
+           "env_steps_per_s_incl_learning": log[-1]["env_steps"] / (time.time() - t0),
+           "success_rate_series": sink.series.get("success_rate", []), "log": log}
+print(json.dumps({k: v for k, v in summary.items() if k != "log"}))
+if out:
+    json.dump(summary, open(out, "w"), indent=1)
