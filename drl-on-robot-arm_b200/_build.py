@@ -41,6 +41,8 @@ def build_libarmsim(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libarmsim.so (no CPU fallback exists)")
     cus = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
     cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_PATH + ".tmp"] + cus
+    if os.environ.get("ARMSIM_SPARSE_MIN_BLOCKS"):   # tuning experiments only
+        cmd.insert(1, "-DARMSIM_SPARSE_MIN_BLOCKS=" + os.environ["ARMSIM_SPARSE_MIN_BLOCKS"])
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

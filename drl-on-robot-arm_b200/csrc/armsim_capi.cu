@@ -236,7 +236,10 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
 // the parameter-driven one
 #define ARMSIM_STEP_CASE(TASK, ROBOT)                                                                           \
   case (TASK) * 4 + (ROBOT):                                                                                    \
-    launch_k(step_lane_kernel<TASK, ROBOT>, grid, st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+    if (!TaskTraits<TASK>::HAS_CUBE && grid > DENSE_GRID_THRESHOLD)                                                   \
+      launch_k(step_lane_kernel<TASK, ROBOT, !TaskTraits<TASK>::HAS_CUBE>, grid, st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+    else                                                                                                          \
+      launch_k(step_lane_kernel<TASK, ROBOT, false>, grid, st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     break;
 
 #define ARMSIM_TORQUE_CASE(TASK, ROBOT)                                                                                \

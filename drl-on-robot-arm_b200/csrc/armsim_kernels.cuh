@@ -11,6 +11,15 @@
 #include "cube_model.cuh"
 
 constexpr int LANE_BLOCK = 128;
+// Two builds of the reach-type step kernels: the default one takes the registers it wants (128, no spills: shortest
+// dependent chain; 4 resident blocks per SM, what a single wave needs) and a "dense" one capped at 80 registers for
+// 6 resident blocks per SM (a few spills, but 50% more warps to hide latency with).  Measured on B200, round 1:
+// dense is +8% env-steps/s at N >= 1M and -7% at N = 4096.  launch_step picks by grid size.
+#ifndef ARMSIM_SPARSE_MIN_BLOCKS
+#define ARMSIM_SPARSE_MIN_BLOCKS 1
+#endif
+constexpr int DENSE_MIN_BLOCKS = 6;
+constexpr int DENSE_GRID_THRESHOLD = 148 * 4;   // more blocks than one wave of the default build
 
 template <int TASK>
 struct TaskTraits {
@@ -268,8 +277,8 @@ __device__ __forceinline__ void notify_host(const HostNotify& H) {
 // its [32,3] action rows and [32,OBS] observation rows through its own slice of shared memory (row-major caller
 // layout <-> one-value-per-lane), ordered by __syncwarp only -- no block-wide barrier on the device path, so warps
 // never wait for each other's HBM latency.
-template <int TASK, int ROBOT>
-__global__ void __launch_bounds__(LANE_BLOCK)
+template <int TASK, int ROBOT, bool DENSE = false>
+__global__ void __launch_bounds__(LANE_BLOCK, DENSE ? DENSE_MIN_BLOCKS : ARMSIM_SPARSE_MIN_BLOCKS)
 step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T, const StatePtrs S,
                  const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
                  uint8_t* __restrict__ done, uint8_t* __restrict__ success, float* __restrict__ final_obs,
