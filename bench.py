@@ -30,6 +30,7 @@ import numpy as np
 N_ENVS = 4096
 ALGO_BYTES = {"reach": 118, "push": 242, "pick": 250, "kuka_reach": 106}    # SURVEY 8(d), per env-step
 L2_BYTES = 126 * 1024 * 1024
+N_ACT = 61                                                                   # action sets in rotation (prime)
 METRIC = "env-steps/sec (reach, N_envs=4096)"
 UNIT = "env-steps/s"
 
@@ -220,7 +221,7 @@ def time_graph(torch, envs, actions, steps, warmup, stream):
 
     def launch_range(lo, hi):
         for k in range(lo, hi):
-            envs[k % pool].step(actions[k % pool])
+            envs[k % pool].step(actions[k % len(actions)])
     with torch.cuda.stream(stream):
         launch_range(0, max(warmup, 3))                       # eager warm-up (also first-use init)
     stream.synchronize()
@@ -254,7 +255,10 @@ def run_ours(args):
     envs = [pkg.BatchedArmEnv(task, n_envs=n, device=dev, seed=0, auto_reset=True,
                               env_id_offset=(rank * pool + b) * n) for b in range(pool)]
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
-    actions = (torch.rand((pool, n, 3), device=dev, generator=gen) * 1.4 - 0.7).contiguous()
+    # a ring of N_ACT independent U(-0.7,0.7) action sets (pre-generated [T,N,3]); launch k uses set k % N_ACT,
+    # N_ACT coprime with the pool size so every env sees a different action at each of its steps (a constant action
+    # would walk every arm into a workspace corner, where the IK needs its full 20 iterations)
+    actions = (torch.rand((N_ACT, n, 3), device=dev, generator=gen) * 1.4 - 0.7).contiguous()
     stream = torch.cuda.Stream(device=dev)
     launches0 = sum(e.launch_count for e in envs)
 
@@ -295,7 +299,7 @@ def run_ours(args):
     bufs = []
     for b in range(e2e_pool):
         hb = envs[b].host_buffers()
-        hb[0][:] = actions[b].cpu().numpy()
+        hb[0][:] = actions[b % len(actions)].cpu().numpy()
         bufs.append(hb)
     for k in range(max(warmup, 3) + e2e_pool):
         envs[k % e2e_pool].step_pinned()
@@ -308,6 +312,23 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     e2e_sec = time.perf_counter() - t0
     barrier()
+    # ---- secondary: the same end-to-end step as a depth-2 pipeline over two independent 4096-env groups
+    # (armsim_step_host_async / _wait, gym.vector's step_async / step_wait): group B's launch + PCIe round trip is in
+    # flight while the host consumes group A's results.  NOT the headline: twice the envs are live at any time.
+    pipe_sec = None
+    if e2e_pool >= 2:
+        ea, eb = envs[0], envs[1]
+        for k in range(6):
+            ea.step_async(); eb.step_async(); ea.step_wait(); eb.step_wait()
+        t0 = time.perf_counter()
+        ea.step_async()
+        for k in range(e2e_steps // 2):
+            eb.step_async()
+            acc += float(ea.step_wait()[1][0])
+            ea.step_async()
+            acc += float(eb.step_wait()[1][0])
+        ea.step_wait()
+        pipe_sec = (time.perf_counter() - t0) / (2 * (e2e_steps // 2) + 1)
     clocks = sampler.stop()
 
     if world > 1:
@@ -333,7 +354,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "rl_%s_env N_envs=%d fused-step kernel, %d x B200 (%d envs total)" % (task, n, world, world * n),
                        "task": task, "n_envs_per_gpu": n, "robot": "kuka_iiwa", "mode": "ik_teleport", "mapping": "lane",
-                       "actions": "pre-generated U(-0.7,0.7) [pool,N,3] f32 on device, auto-reset in kernel",
+                       "actions": "pre-generated U(-0.7,0.7) [%d,N,3] f32 on device (launch k uses set k mod %d), auto-reset in kernel" % (N_ACT, N_ACT),
                        "l2": "inputs larger than L2: round-robin over a pool of %d independent %d-env batches "
                              "(%.0f MB touched state, L2 = 126 MB), every launch HBM-cold" % (pool, n, pool * abytes * n / 1e6),
                        "launch": "CUDA graph of exactly K fused-step launches, CUDA events on the launching stream"},
@@ -346,7 +367,10 @@ def run_ours(args):
                                  "dependent fp32 per 118 B"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "ArmSimHandle.step_pinned -> armsim_step_host on the handle's pinned host block "
-                           "(armsim_host_buffers): graph-replayed kernel reads actions / writes results over PCIe, per-block doorbells"},
+                           "(armsim_host_buffers): graph-replayed kernel reads actions / writes results over PCIe, per-block doorbells",
+                    "pipelined_depth2": None if pipe_sec is None else
+                    {"value": world * n / pipe_sec, "unit": UNIT, "note": "secondary: step_async/step_wait over two independent "
+                     "%d-env groups per GPU (same per-step H2D/D2H bytes); the headline e2e above is the synchronous call" % n}},
             "gpu_launches": steps,
             "clocks": clocks,
         }
@@ -373,21 +397,27 @@ def side_measurements(torch, pkg, dev, peak_gbs):
             k = 20 * pool if n >= (1 << 20) else 600
             envs = [pkg.BatchedArmEnv(task, n_envs=n, device=dev, seed=0, auto_reset=True, env_id_offset=b * n)
                     for b in range(pool)]
-            a = (torch.rand((pool, n, 3), device=dev) * 1.4 - 0.7)
+            na = 7 if n >= (1 << 20) else N_ACT
+            if pool % na == 0:
+                na -= 1                                          # keep the ring out of step with the pool
+            k = max(na, k // na * na)                            # whole turns of the action ring per replay
+            a = (torch.rand((na, n, 3), device=dev) * 1.4 - 0.7)
             if task != "reach":
                 a *= 0.4 / 0.7                                  # action_bound 0.4 for push / pick (main.py:457,526)
             with torch.cuda.stream(stream):
                 for j in range(max(3, min(pool, 8))):
-                    envs[j % pool].step(a[j % pool])
+                    envs[j % pool].step(a[j % na])
             stream.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
                 for j in range(k):
-                    envs[j % pool].step(a[j % pool])
+                    envs[j % pool].step(a[j % na])
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(stream):
-                g.replay()                                       # advances every env past the reset transient
-                stream.synchronize()
+                t_end = time.time() + 0.25                       # untimed: past the reset transient, clocks ramped up
+                while time.time() < t_end:
+                    g.replay()
+                    stream.synchronize()
                 e0.record(stream)
                 g.replay()
                 e1.record(stream)

@@ -23,7 +23,7 @@ EXPORTS = [
     "armsim_abi_version", "armsim_last_error", "armsim_default_config", "armsim_create", "armsim_destroy",
     "armsim_reset", "armsim_step", "armsim_step_host", "armsim_reset_host", "armsim_set_state", "armsim_get_state",
     "armsim_obs_dim", "armsim_action_dim", "armsim_n_envs", "armsim_mapping", "armsim_launch_count", "armsim_fk_host",
-    "armsim_host_buffers", "armsim_step_ex",
+    "armsim_host_buffers", "armsim_step_ex", "armsim_step_host_async", "armsim_step_host_wait",
     "armsim_replay_create", "armsim_replay_destroy", "armsim_replay_begin", "armsim_replay_store", "armsim_replay_sample",
     "armsim_replay_gather", "armsim_replay_info", "armsim_replay_table", "armsim_replay_last_error",
     "armsim_replay_state_bytes", "armsim_replay_get_state", "armsim_replay_set_state",
@@ -90,6 +90,8 @@ def lib():
     L.armsim_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.armsim_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.armsim_step_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.armsim_step_host_async.argtypes = [vp, vp]
+    L.armsim_step_host_wait.argtypes = [vp, vp, vp, vp, vp]
     L.armsim_reset_host.argtypes = [vp, vp, vp]
     L.armsim_host_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
     L.armsim_set_state.argtypes = [vp, i32, vp, C.c_size_t]

@@ -50,6 +50,7 @@ struct ArmSim {
   bool zero_copy = true;
   cudaGraphExec_t host_graph = nullptr;   // the zero-copy host step as an instantiated graph (parameters never change)
   bool host_graph_tried = false;
+  bool host_pending = false;              // armsim_step_host_async issued, armsim_step_host_wait not yet
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
 };
@@ -236,8 +237,8 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
 // the parameter-driven one
 #define ARMSIM_STEP_CASE(TASK, ROBOT)                                                                           \
   case (TASK) * 4 + (ROBOT):                                                                                    \
-    if (!TaskTraits<TASK>::HAS_CUBE && grid > DENSE_GRID_THRESHOLD)                                                   \
-      launch_k(step_lane_kernel<TASK, ROBOT, !TaskTraits<TASK>::HAS_CUBE>, grid, st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+    if (grid > (TaskTraits<TASK>::HAS_CUBE ? DENSE_GRID_THRESHOLD_CUBE : DENSE_GRID_THRESHOLD))                       \
+      launch_k(step_lane_kernel<TASK, ROBOT, true>, grid, st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     else                                                                                                          \
       launch_k(step_lane_kernel<TASK, ROBOT, false>, grid, st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     break;
@@ -452,18 +453,16 @@ int armsim_step_ex(ArmSim* s, const float* action_dev, float* obs_dev, float* re
                      final_obs_dev);
 }
 
-int armsim_step_host(ArmSim* s, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host,
-                     uint8_t* success_host) {
-  if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_host: null handle");
-  if (!action_host || !obs_host || !reward_host || !done_host || !success_host) return fail(ARMSIM_E_INVALID, "armsim_step_host: null buffer");
-  CU(cudaSetDevice(s->cfg.device));
+// First half of the host step: stage the actions (unless they already sit in the pinned block) and put the fused
+// launch in flight.  Zero-copy path: one graph launch, nothing else; DMA path (n > 65536): H2D + launch + D2H queued.
+static int host_step_submit(ArmSim* s, const float* action_host) {
   const size_t n = (size_t)s->n;
   char* h_out = s->h_pin + s->act_bytes;
   char* d_out = s->d_io + s->act_bytes;
+  if (s->host_pending) return fail(ARMSIM_E_STATE, "armsim_step_host_async: the previous step has not been waited for");
   // callers that work in the handle's own pinned block (armsim_host_buffers) skip the staging memcpys
   if ((const char*)action_host != s->h_pin) memcpy(s->h_pin, action_host, n * s->act_dim * 4);
   if (s->zero_copy) {
-    const unsigned int seq = ++s->seq;
     HostNotify H{s->d_cta_seq, (unsigned int*)s->h_flags};
     float* o = (float*)(h_out + s->off_obs);
     float* r = (float*)(h_out + s->off_reward);
@@ -484,22 +483,35 @@ int armsim_step_host(ArmSim* s, const float* action_host, float* obs_host, float
         cudaGetLastError();
       }
     }
-    int rc = ARMSIM_OK;
     if (s->host_graph) {
       CU(cudaGraphLaunch(s->host_graph, s->stream));
       s->launches += 1;
     } else {
-      rc = launch_step(s, (const float*)s->h_pin, o, r, d, su, s->stream, H);
+      int rc = launch_step(s, (const float*)s->h_pin, o, r, d, su, s->stream, H);
+      if (rc) return rc;
     }
-    if (rc) return rc;
-    rc = wait_doorbells(s, seq);
-    if (rc) return rc;
+    ++s->seq;
   } else {
     CU(cudaMemcpyAsync(s->d_io, s->h_pin, n * s->act_dim * 4, cudaMemcpyHostToDevice, s->stream));
     int rc = launch_step(s, (const float*)s->d_io, (float*)(d_out + s->off_obs), (float*)(d_out + s->off_reward),
                          (uint8_t*)(d_out + s->off_done), (uint8_t*)(d_out + s->off_success), s->stream);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h_out, d_out, s->out_bytes, cudaMemcpyDeviceToHost, s->stream));
+  }
+  s->host_pending = true;
+  return ARMSIM_OK;
+}
+
+// Second half: block until the results are readable in the pinned block, then hand them to the caller's buffers.
+static int host_step_wait(ArmSim* s, float* obs_host, float* reward_host, uint8_t* done_host, uint8_t* success_host) {
+  const size_t n = (size_t)s->n;
+  char* h_out = s->h_pin + s->act_bytes;
+  if (!s->host_pending) return fail(ARMSIM_E_STATE, "armsim_step_host_wait: no step in flight");
+  s->host_pending = false;
+  if (s->zero_copy) {
+    int rc = wait_doorbells(s, s->seq);
+    if (rc) return rc;
+  } else {
     CU(cudaStreamSynchronize(s->stream));
   }
   if ((char*)obs_host != h_out + s->off_obs) memcpy(obs_host, h_out + s->off_obs, n * s->obs_dim * 4);
@@ -507,6 +519,28 @@ int armsim_step_host(ArmSim* s, const float* action_host, float* obs_host, float
   if ((char*)done_host != h_out + s->off_done) memcpy(done_host, h_out + s->off_done, n);
   if ((char*)success_host != h_out + s->off_success) memcpy(success_host, h_out + s->off_success, n);
   return ARMSIM_OK;
+}
+
+int armsim_step_host(ArmSim* s, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                     uint8_t* success_host) {
+  if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_host: null handle");
+  if (!action_host || !obs_host || !reward_host || !done_host || !success_host) return fail(ARMSIM_E_INVALID, "armsim_step_host: null buffer");
+  CU(cudaSetDevice(s->cfg.device));
+  int rc = host_step_submit(s, action_host);
+  if (rc) return rc;
+  return host_step_wait(s, obs_host, reward_host, done_host, success_host);
+}
+
+int armsim_step_host_async(ArmSim* s, const float* action_host) {
+  if (!s || !action_host) return fail(ARMSIM_E_INVALID, "armsim_step_host_async: null argument");
+  CU(cudaSetDevice(s->cfg.device));
+  return host_step_submit(s, action_host);
+}
+
+int armsim_step_host_wait(ArmSim* s, float* obs_host, float* reward_host, uint8_t* done_host, uint8_t* success_host) {
+  if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_host_wait: null handle");
+  if (!obs_host || !reward_host || !done_host || !success_host) return fail(ARMSIM_E_INVALID, "armsim_step_host_wait: null buffer");
+  return host_step_wait(s, obs_host, reward_host, done_host, success_host);
 }
 
 int armsim_reset_host(ArmSim* s, const uint8_t* mask_host, float* obs_host) {

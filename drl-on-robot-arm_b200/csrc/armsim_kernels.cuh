@@ -19,7 +19,9 @@ constexpr int LANE_BLOCK = 128;
 #define ARMSIM_SPARSE_MIN_BLOCKS 1
 #endif
 constexpr int DENSE_MIN_BLOCKS = 6;
-constexpr int DENSE_GRID_THRESHOLD = 148 * 4;   // more blocks than one wave of the default build
+constexpr int DENSE_MIN_BLOCKS_CUBE = 3;        // push / pick: 223 / 255 registers by default, <= 168 when dense
+constexpr int DENSE_GRID_THRESHOLD = 148 * 4;   // more blocks than one wave of the default reach build
+constexpr int DENSE_GRID_THRESHOLD_CUBE = 148 * 2;
 
 template <int TASK>
 struct TaskTraits {
@@ -278,7 +280,8 @@ __device__ __forceinline__ void notify_host(const HostNotify& H) {
 // layout <-> one-value-per-lane), ordered by __syncwarp only -- no block-wide barrier on the device path, so warps
 // never wait for each other's HBM latency.
 template <int TASK, int ROBOT, bool DENSE = false>
-__global__ void __launch_bounds__(LANE_BLOCK, DENSE ? DENSE_MIN_BLOCKS : ARMSIM_SPARSE_MIN_BLOCKS)
+__global__ void __launch_bounds__(LANE_BLOCK, DENSE ? (TaskTraits<TASK>::HAS_CUBE ? DENSE_MIN_BLOCKS_CUBE : DENSE_MIN_BLOCKS)
+                                                    : ARMSIM_SPARSE_MIN_BLOCKS)
 step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T, const StatePtrs S,
                  const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
                  uint8_t* __restrict__ done, uint8_t* __restrict__ success, float* __restrict__ final_obs,

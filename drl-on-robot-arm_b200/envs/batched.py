@@ -119,6 +119,33 @@ class ArmSimHandle:
         call()
         return self._hb[1:]
 
+    def step_async(self):
+        """gym.vector's step_async on the pinned block: actions are read from host_buffers()[0]; returns at once"""
+        calls = getattr(self, "_async_calls", None)
+        if calls is None:
+            hb = self.host_buffers()
+            lib = L.lib()
+            h, a = self.h, C.c_void_p(hb[0].ctypes.data)
+            outs = tuple(C.c_void_p(b.ctypes.data) for b in hb[1:])
+            fa, fw, chk = lib.armsim_step_host_async, lib.armsim_step_host_wait, L.check
+
+            def submit():
+                rc = fa(h, a)
+                if rc:
+                    chk(rc)
+
+            def wait():
+                rc = fw(h, *outs)
+                if rc:
+                    chk(rc)
+            calls = self._async_calls = (submit, wait)
+        calls[0]()
+
+    def step_wait(self):
+        """gym.vector's step_wait: blocks until the step issued by step_async has landed in host_buffers()[1:]"""
+        self._async_calls[1]()
+        return self._hb[1:]
+
     def step_host(self, action, out=None):
         a = action if (isinstance(action, np.ndarray) and action.dtype == np.float32 and action.flags.c_contiguous) \
             else np.ascontiguousarray(action, np.float32)

@@ -150,6 +150,13 @@ int armsim_step_host(ArmSim* sim, const float* action_host, float* obs_host, flo
                      uint8_t* success_host);
 int armsim_reset_host(ArmSim* sim, const uint8_t* mask_host, float* obs_host);
 
+/* The same call split in two, gym.vector's step_async / step_wait: _async stages the actions and puts the launch in
+ * flight, _wait blocks until the results are in the caller's buffers.  A host loop that owns two (or more) handles
+ * can overlap one group's launch + PCIe round trip with its own work on the other group's results.  At most one step
+ * per handle may be in flight (ARMSIM_E_STATE otherwise).  No counterpart in the reference (single env, synchronous). */
+int armsim_step_host_async(ArmSim* sim, const float* action_host);
+int armsim_step_host_wait(ArmSim* sim, float* obs_host, float* reward_host, uint8_t* done_host, uint8_t* success_host);
+
 /* The handle's own pinned (page-locked, device-mapped) I/O block: action f32 [n, act_dim], obs f32 [n, obs_dim],
  * reward f32 [n], done u8 [n], success u8 [n].  Passing exactly these pointers to armsim_step_host makes the call
  * copy-free on the host: for n_envs <= 65536 the kernel reads the actions from and writes the results to this block

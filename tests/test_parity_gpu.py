@@ -413,6 +413,34 @@ def test_host_doorbells_never_publish_stale_results(pkg, torch_cuda):
     h.close(); e.close()
 
 
+def test_step_async_wait_pipeline_equals_sync(pkg, torch_cuda):
+    """armsim_step_host_async / _wait (gym.vector step_async / step_wait): two handles stepped as a depth-2 pipeline give
+    the same bits as the synchronous call; a second submit without a wait is refused; the DMA route (n > 65536) too"""
+    for n in (512, 66000):
+        rng = np.random.default_rng(n)
+        acts = rng.uniform(-0.7, 0.7, (6, 2, n, 3)).astype(np.float32)
+        pipe = [pkg.ArmSimHandle("reach", n_envs=n, seed=21 + i, auto_reset=True) for i in range(2)]
+        sync = [pkg.ArmSimHandle("reach", n_envs=n, seed=21 + i, auto_reset=True) for i in range(2)]
+        bufs = [h.host_buffers() for h in pipe]
+        bufs[0][0][:] = acts[0, 0]
+        pipe[0].step_async()
+        with pytest.raises(pkg._lib.ArmsimError):
+            pipe[0].step_async()
+        for k in range(6):
+            for i in range(2):
+                nxt = (k * 2 + i + 1)
+                if nxt < 12:                                      # keep the other handle's step in flight while we wait
+                    bufs[nxt % 2][0][:] = acts[nxt // 2, nxt % 2]
+                    pipe[nxt % 2].step_async()
+                o, r, d, s_ = pipe[i].step_wait()
+                o2, r2, d2, s2 = sync[i].step_host(acts[k, i])
+                assert np.array_equal(o, o2) and np.array_equal(r, r2) and np.array_equal(d, d2) and np.array_equal(s_, s2)
+        with pytest.raises(pkg._lib.ArmsimError):
+            pipe[0].step_wait()
+        for h in pipe + sync:
+            h.close()
+
+
 def test_host_path_large_batch_uses_dma_copies(pkg, torch_cuda):
     """n > 65536 takes the cudaMemcpyAsync route of armsim_step_host; same results as the device-pointer path"""
     torch = torch_cuda

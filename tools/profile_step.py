@@ -7,10 +7,11 @@ import drl_on_robot_arm_b200 as pkg
 
 task, n, pool, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 envs = [pkg.BatchedArmEnv(task, n_envs=n, device="cuda:0", seed=0, auto_reset=True, env_id_offset=b * n) for b in range(pool)]
-acts = torch.rand((pool, n, 3), device="cuda") * 1.4 - 0.7
+NA = 7 if n >= (1 << 20) else 61   # action sets in rotation: every env sees a different action at each step
+acts = torch.rand((NA, n, 3), device="cuda") * 1.4 - 0.7
 if task != "reach":
     acts *= 0.4 / 0.7
 for k in range(steps):
-    envs[k % pool].step(acts[k % pool])
+    envs[k % pool].step(acts[k % NA])
 torch.cuda.synchronize()
 print("done", task, n, pool, steps)
