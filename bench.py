@@ -39,7 +39,7 @@ def load_traffic(task, n):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None"""
     p = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
     try:
-        d = json.load(open(p))["v3_%s_n%d" % (task, n)]
+        d = json.load(open(p))["v5_%s_n%d" % (task, n)]
         return d["dram__bytes_read.sum"]["value"] * {"Kbyte": 1e3, "Mbyte": 1e6, "byte": 1.0}[d["dram__bytes_read.sum"]["unit"]] + \
             d["dram__bytes_write.sum"]["value"] * {"Kbyte": 1e3, "Mbyte": 1e6, "byte": 1.0}[d["dram__bytes_write.sum"]["unit"]]
     except Exception:
@@ -363,8 +363,9 @@ def run_ours(args):
                          "profiles/r01_ncu_summary.json; writes still in L2 at kernel end are not counted by ncu)",
                          "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
                          "kernel": "step_lane_kernel<%s>" % task, "avg_launch_us": launch_us,
-                         "note": "kernel is fp32-issue / launch-latency bound, not HBM bound (SURVEY 7): ~6 kFLOP of "
-                                 "dependent fp32 per 118 B"},
+                         "note": "kernel is fp32-issue / dependent-latency bound, not HBM bound (SURVEY 7): ~6 kFLOP of "
+                                 "dependent fp32 per 118 B; at N=4096 128 warps on 592 SM sub-partitions wait for the "
+                                 "slowest arm's IK (3 DLS iterations typical); see other_configs for the multi-wave sizes"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "ArmSimHandle.step_pinned -> armsim_step_host on the handle's pinned host block "
                            "(armsim_host_buffers): graph-replayed kernel reads actions / writes results over PCIe, per-block doorbells",

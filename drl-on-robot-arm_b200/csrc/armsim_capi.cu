@@ -174,12 +174,20 @@ static bool pdl_enabled() {
   return v == 1;
 }
 
+// Dynamic shared memory of a kernel that may step a cube (per-thread contact slots, cube_model.cuh): 64 KB per block,
+// above the 48 KB default, so every such kernel function opts in once.
+template <class F>
+static void ensure_smem(F kern, size_t bytes) {
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 template <class... KArgs, class... Args>
-static void launch_k(void (*kern)(KArgs...), int grid, cudaStream_t st, bool pdl, Args... args) {
+static void launch_k(void (*kern)(KArgs...), int grid, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  ensure_smem(kern, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(LANE_BLOCK);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -188,6 +196,9 @@ static void launch_k(void (*kern)(KArgs...), int grid, cudaStream_t st, bool pdl
   cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
+
+template <int TASK>
+constexpr size_t task_smem() { return TaskTraits<TASK>::HAS_CUBE ? (size_t)cube::SCRATCH_BYTES : 0; }
 
 extern "C" {
 
@@ -222,10 +233,10 @@ void armsim_destroy(ArmSim* s) {
 static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cudaStream_t st) {
   const int grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
   switch (s->cfg.task) {
-    case ARMSIM_TASK_REACH: reset_lane_kernel<ARMSIM_TASK_REACH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
-    case ARMSIM_TASK_PUSH: reset_lane_kernel<ARMSIM_TASK_PUSH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
-    case ARMSIM_TASK_PICK: reset_lane_kernel<ARMSIM_TASK_PICK><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
-    case ARMSIM_TASK_KUKA_REACH: reset_lane_kernel<ARMSIM_TASK_KUKA_REACH><<<grid, LANE_BLOCK, 0, st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
+    case ARMSIM_TASK_REACH: ensure_smem(reset_lane_kernel<ARMSIM_TASK_REACH>, task_smem<ARMSIM_TASK_REACH>()); reset_lane_kernel<ARMSIM_TASK_REACH><<<grid, LANE_BLOCK, task_smem<ARMSIM_TASK_REACH>(), st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
+    case ARMSIM_TASK_PUSH: ensure_smem(reset_lane_kernel<ARMSIM_TASK_PUSH>, task_smem<ARMSIM_TASK_PUSH>()); reset_lane_kernel<ARMSIM_TASK_PUSH><<<grid, LANE_BLOCK, task_smem<ARMSIM_TASK_PUSH>(), st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
+    case ARMSIM_TASK_PICK: ensure_smem(reset_lane_kernel<ARMSIM_TASK_PICK>, task_smem<ARMSIM_TASK_PICK>()); reset_lane_kernel<ARMSIM_TASK_PICK><<<grid, LANE_BLOCK, task_smem<ARMSIM_TASK_PICK>(), st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
+    case ARMSIM_TASK_KUKA_REACH: ensure_smem(reset_lane_kernel<ARMSIM_TASK_KUKA_REACH>, task_smem<ARMSIM_TASK_KUKA_REACH>()); reset_lane_kernel<ARMSIM_TASK_KUKA_REACH><<<grid, LANE_BLOCK, task_smem<ARMSIM_TASK_KUKA_REACH>(), st>>>(s->chain, s->task, s->S, mask_dev, obs_dev); break;
     default: return fail(ARMSIM_E_INVALID, "bad task");
   }
   s->launches += 1;
@@ -238,14 +249,14 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
 #define ARMSIM_STEP_CASE(TASK, ROBOT)                                                                           \
   case (TASK) * 4 + (ROBOT):                                                                                    \
     if (grid > (TaskTraits<TASK>::HAS_CUBE ? DENSE_GRID_THRESHOLD_CUBE : DENSE_GRID_THRESHOLD))                       \
-      launch_k(step_lane_kernel<TASK, ROBOT, true>, grid, st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+      launch_k(step_lane_kernel<TASK, ROBOT, true>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     else                                                                                                          \
-      launch_k(step_lane_kernel<TASK, ROBOT, false>, grid, st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+      launch_k(step_lane_kernel<TASK, ROBOT, false>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     break;
 
 #define ARMSIM_TORQUE_CASE(TASK, ROBOT)                                                                                \
   case (TASK) * 4 + (ROBOT):                                                                                           \
-    launch_k(step_torque_kernel<TASK, ROBOT>, grid, st, H.flags == nullptr, s->chain, s->task, s->dyn, s->S, a, o, r, d, su, fo, H); \
+    launch_k(step_torque_kernel<TASK, ROBOT>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->dyn, s->S, a, o, r, d, su, fo, H); \
     break;
 
 static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st,

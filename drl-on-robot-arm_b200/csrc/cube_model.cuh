@@ -146,12 +146,27 @@ __device__ __forceinline__ float gripper_distance(const State& cb, const float (
   return best;
 }
 
-// One projected-Gauss-Seidel row for a general direction (arm-proxy contacts).  rxd = r x dir and 1/k do not change
-// between sweeps but are recomputed (9 instructions) instead of held: registers are the scarcer resource here.
-__device__ __forceinline__ void row(State& cb, const float (&r)[3], const float (&dir)[3], float target, float lo, float hi,
-                                    float& acc) {
+// ---- per-thread contact slots in shared memory ---------------------------------------------------------------------
+// Every contact of the oracle's list has a STATIC slot -- 8 corner slots + 3 proxy slots with an "active" bit -- in a
+// per-thread column of dynamic shared memory: word k of the calling thread is scratch[k * SLOT_STRIDE + threadIdx.x]
+// (conflict-free: a warp reads 32 consecutive words).  Offsets are compile-time constants after unrolling, so a
+// sweep is LDS/STS with immediate offsets + a handful of FMAs per row; the cube's velocity state stays in registers.
+// (Round 1 history: a compacted, dynamically indexed contact array lived in local memory, ~170 instructions per
+// contact per sweep; static slots in registers made ptxas rematerialise the corner geometry inside the sweep loop,
+// ~70-85; the shared-memory slots are ~50 and cut the kernel from 223 to ~120 registers.)
+constexpr int SLOT_STRIDE = 128;                 // = LANE_BLOCK (threads per block of every kernel that steps cubes)
+constexpr int CORNER_WORDS = 10;                 // r[3], bias, 1/k for n, t1, t2, lambda n, t1, t2
+constexpr int PROXY_WORDS = 16;                  // r[3], n[3], t1[3], t2[3], bias, lambda n, t1, t2
+constexpr int SCRATCH_WORDS = 8 * CORNER_WORDS + 3 * PROXY_WORDS;
+constexpr int SCRATCH_BYTES = SCRATCH_WORDS * SLOT_STRIDE * 4;     // 64 KB per 128-thread block
+
+extern __shared__ float cube_scratch[];
+
+// One projected-Gauss-Seidel row for a general direction (arm-proxy contacts); v, w = cube twist (registers).
+__device__ __forceinline__ void row(float (&v)[3], float (&w)[3], const float (&r)[3], const float (&dir)[3], float target,
+                                    float lo, float hi, float& acc) {
   const float rxd[3] = {r[1] * dir[2] - r[2] * dir[1], r[2] * dir[0] - r[0] * dir[2], r[0] * dir[1] - r[1] * dir[0]};
-  const float vrel = dir[0] * cb.v[0] + dir[1] * cb.v[1] + dir[2] * cb.v[2] + rxd[0] * cb.w[0] + rxd[1] * cb.w[1] + rxd[2] * cb.w[2];
+  const float vrel = dir[0] * v[0] + dir[1] * v[1] + dir[2] * v[2] + rxd[0] * w[0] + rxd[1] * w[1] + rxd[2] * w[2];
   const float k = fmaf(rxd[0] * rxd[0] + rxd[1] * rxd[1] + rxd[2] * rxd[2], INV_INERTIA, INV_MASS);
   float dl = (target - vrel) * rcp_approx(k);
   const float nl = fminf(fmaxf(acc + dl, lo), hi);
@@ -160,146 +175,164 @@ __device__ __forceinline__ void row(State& cb, const float (&r)[3], const float 
   const float dli = dl * INV_INERTIA;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    cb.v[i] = fmaf(dl, dir[i], cb.v[i]);      // INV_MASS = 1
-    cb.w[i] = fmaf(dli, rxd[i], cb.w[i]);
+    v[i] = fmaf(dl, dir[i], v[i]);      // INV_MASS = 1
+    w[i] = fmaf(dli, rxd[i], w[i]);
   }
 }
 
 // The three rows of a cube-corner / table contact.  The plane normal is +z, for which btPlaneSpace1 (tangents()) gives
 // t1 = (0,-1,0), t2 = (1,0,0); r x dir is then a signed permutation of r and the generic row collapses to a handful
 // of FMAs.  ik* = 1 / (1/m + |r x dir|^2 / I) per row, computed once per step.
-__device__ __forceinline__ void table_rows(State& cb, float r0, float r1, float r2, float bias, float ikn, float ik1, float ik2,
-                                           float& ln, float& l1, float& l2) {
+__device__ __forceinline__ void table_rows(float (&v)[3], float (&w)[3], float r0, float r1, float r2, float bias, float ikn,
+                                           float ik1, float ik2, float& ln, float& l1, float& l2) {
   const float r0i = r0 * INV_INERTIA, r1i = r1 * INV_INERTIA, r2i = r2 * INV_INERTIA;
   {  // normal (0,0,1): r x n = (r1, -r0, 0)
-    const float vrel = fmaf(r1, cb.w[0], fmaf(-r0, cb.w[1], cb.v[2]));
+    const float vrel = fmaf(r1, w[0], fmaf(-r0, w[1], v[2]));
     const float nl = fminf(fmaxf(fmaf(bias - vrel, ikn, ln), 0.0f), 1e30f);
     const float dl = nl - ln;
     ln = nl;
-    cb.v[2] += dl;
-    cb.w[0] = fmaf(dl, r1i, cb.w[0]);
-    cb.w[1] = fmaf(-dl, r0i, cb.w[1]);
+    v[2] += dl;
+    w[0] = fmaf(dl, r1i, w[0]);
+    w[1] = fmaf(-dl, r0i, w[1]);
   }
   const float lim = MU * ln;
   {  // t1 = (0,-1,0): r x t1 = (r2, 0, -r0)
-    const float vrel = fmaf(r2, cb.w[0], fmaf(-r0, cb.w[2], -cb.v[1]));
+    const float vrel = fmaf(r2, w[0], fmaf(-r0, w[2], -v[1]));
     const float nl = fminf(fmaxf(fmaf(-vrel, ik1, l1), -lim), lim);
     const float dl = nl - l1;
     l1 = nl;
-    cb.v[1] -= dl;
-    cb.w[0] = fmaf(dl, r2i, cb.w[0]);
-    cb.w[2] = fmaf(-dl, r0i, cb.w[2]);
+    v[1] -= dl;
+    w[0] = fmaf(dl, r2i, w[0]);
+    w[2] = fmaf(-dl, r0i, w[2]);
   }
   {  // t2 = (1,0,0): r x t2 = (0, r2, -r1)
-    const float vrel = fmaf(r2, cb.w[1], fmaf(-r1, cb.w[2], cb.v[0]));
+    const float vrel = fmaf(r2, w[1], fmaf(-r1, w[2], v[0]));
     const float nl = fminf(fmaxf(fmaf(-vrel, ik2, l2), -lim), lim);
     const float dl = nl - l2;
     l2 = nl;
-    cb.v[0] += dl;
-    cb.w[1] = fmaf(dl, r2i, cb.w[1]);
-    cb.w[2] = fmaf(-dl, r1i, cb.w[2]);
+    v[0] += dl;
+    w[1] = fmaf(dl, r2i, w[1]);
+    w[2] = fmaf(-dl, r1i, w[2]);
   }
 }
 
-// one p.stepSimulation() for the cube; grip: 0 open / push, 1 closed, 2 holding.
-//
-// Same contact list and the same Gauss-Seidel order as oracle/cube_model.h (corners 0..7 in index order, then the arm
-// proxies), but every contact has a STATIC slot -- 8 corner slots + NP proxy slots with an "active" bit -- instead of
-// a compacted array: the slots are indexed by unrolled compile-time constants, so the whole contact set lives in
-// registers (the compacted, dynamically indexed array of round 1's first version lived in local memory: 1 KB stack
-// frame, ~170 instructions per contact per sweep; now ~45 for a corner).  The corner lever arm r is rebuilt from the
-// three half-edge vectors with sign flips (6 FADD) rather than held.
+// one p.stepSimulation() for the cube; grip: 0 open / push, 1 closed, 2 holding.  Same contact list and the same
+// Gauss-Seidel order as oracle/cube_model.h (corners 0..7 in index order, then the arm proxies).  Needs
+// SCRATCH_BYTES of dynamic shared memory in the calling kernel.
 template <bool PICK>
-static __device__ __noinline__ void step(State& cb, const float (&ee)[3], const float (&Ree)[9], float grip) {
+static __device__ __noinline__ void step(State& cbm, const float (&ee)[3], const float (&Ree)[9], float grip) {
   if (PICK && grip >= 1.5f) {
-    cb.pos[0] = ee[0] + GRIPPER_LEN * Ree[2];
-    cb.pos[1] = ee[1] + GRIPPER_LEN * Ree[5];
-    cb.pos[2] = ee[2] + GRIPPER_LEN * Ree[8];
+    cbm.pos[0] = ee[0] + GRIPPER_LEN * Ree[2];
+    cbm.pos[1] = ee[1] + GRIPPER_LEN * Ree[5];
+    cbm.pos[2] = ee[2] + GRIPPER_LEN * Ree[8];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { cb.v[i] = 0.f; cb.w[i] = 0.f; }
+    for (int i = 0; i < 3; ++i) { cbm.v[i] = 0.f; cbm.w[i] = 0.f; }
     return;
   }
-  cb.v[2] -= G * DT;
+  State cb = cbm;                    // work on a register copy (the caller's object lives behind a reference)
+  float v[3], w[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { cb.v[i] *= DAMP; cb.w[i] *= DAMP; }
+  for (int i = 0; i < 3; ++i) { v[i] = cb.v[i] * DAMP; w[i] = cb.w[i] * DAMP; }
+  v[2] = (cb.v[2] - G * DT) * DAMP;
 
+  float* const sm = cube_scratch + threadIdx.x;
   float R[9];
   rot(cb.quat, R);
-  float H[9];                        // half-edge vectors: column k of R times HALF
-#pragma unroll
-  for (int i = 0; i < 9; ++i) H[i] = R[i] * HALF;
-
-  // ---- corner slots
   unsigned active = 0u;
-  float tb[8], tln[8], tl1[8], tl2[8], tkn[8], tk1[8], tk2[8];
+  {
+    float H[9];                      // half-edge vectors: column k of R times HALF
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float r[3];
+    for (int i = 0; i < 9; ++i) H[i] = R[i] * HALF;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-      r[i] = ((c & 1) ? H[3 * i] : -H[3 * i]) + ((c & 2) ? H[3 * i + 1] : -H[3 * i + 1]) + ((c & 4) ? H[3 * i + 2] : -H[3 * i + 2]);
-    const float gap = cb.pos[2] + r[2] - TABLE_Z;
-    if (gap < MARGIN) active |= 1u << c;
-    tb[c] = gap < 0.f ? -ERP * gap * INV_DT : -gap * INV_DT;
-    tln[c] = tl1[c] = tl2[c] = 0.f;
-    const float a = r[0] * r[0], b = r[1] * r[1], d = r[2] * r[2];
-    tkn[c] = rcp_approx(fmaf(a + b, INV_INERTIA, INV_MASS));
-    tk1[c] = rcp_approx(fmaf(d + a, INV_INERTIA, INV_MASS));
-    tk2[c] = rcp_approx(fmaf(d + b, INV_INERTIA, INV_MASS));
-  }
-
-  // ---- arm-proxy slots
-  constexpr int NP = PICK ? 3 : 1;
-  float C[3][3], rad[3];
-  const int np = arm_proxies(ee, Ree, PICK, grip, C, rad);
-  Contact K[NP];
+    for (int c = 0; c < 8; ++c) {
+      float r[3];
 #pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    float rr[3], nn[3];
-    const float d = sphere_query(cb, R, C[p], rad[p], rr, nn);
-    if (p < np && d < 0.f) {
-      active |= 1u << (8 + p);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { K[p].r[i] = rr[i]; K[p].n[i] = nn[i]; }
-      K[p].bias = -ERP * d * INV_DT;
-      tangents(K[p]);
+      for (int i = 0; i < 3; ++i)
+        r[i] = ((c & 1) ? H[3 * i] : -H[3 * i]) + ((c & 2) ? H[3 * i + 1] : -H[3 * i + 1]) + ((c & 4) ? H[3 * i + 2] : -H[3 * i + 2]);
+      const float gap = cb.pos[2] + r[2] - TABLE_Z;
+      if (gap < MARGIN) {
+        active |= 1u << c;
+        float* s = sm + c * CORNER_WORDS * SLOT_STRIDE;
+        const float a = r[0] * r[0], b = r[1] * r[1], d = r[2] * r[2];
+        s[0 * SLOT_STRIDE] = r[0]; s[1 * SLOT_STRIDE] = r[1]; s[2 * SLOT_STRIDE] = r[2];
+        s[3 * SLOT_STRIDE] = gap < 0.f ? -ERP * gap * INV_DT : -gap * INV_DT;
+        s[4 * SLOT_STRIDE] = rcp_approx(fmaf(a + b, INV_INERTIA, INV_MASS));
+        s[5 * SLOT_STRIDE] = rcp_approx(fmaf(d + a, INV_INERTIA, INV_MASS));
+        s[6 * SLOT_STRIDE] = rcp_approx(fmaf(d + b, INV_INERTIA, INV_MASS));
+        s[7 * SLOT_STRIDE] = 0.f; s[8 * SLOT_STRIDE] = 0.f; s[9 * SLOT_STRIDE] = 0.f;
+      }
     }
-    K[p].ln = K[p].l1 = K[p].l2 = 0.f;
+  }
+  {
+    constexpr int NP = PICK ? 3 : 1;
+    float C[3][3], rad[3];
+    const int np = arm_proxies(ee, Ree, PICK, grip, C, rad);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      float rr[3], nn[3];
+      const float d = sphere_query(cb, R, C[p], rad[p], rr, nn);
+      if (p < np && d < 0.f) {
+        active |= 1u << (8 + p);
+        Contact k;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { k.r[i] = rr[i]; k.n[i] = nn[i]; }
+        tangents(k);
+        float* s = sm + (8 * CORNER_WORDS + p * PROXY_WORDS) * SLOT_STRIDE;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          s[(0 + i) * SLOT_STRIDE] = k.r[i]; s[(3 + i) * SLOT_STRIDE] = k.n[i];
+          s[(6 + i) * SLOT_STRIDE] = k.t1[i]; s[(9 + i) * SLOT_STRIDE] = k.t2[i];
+        }
+        s[12 * SLOT_STRIDE] = -ERP * d * INV_DT;
+        s[13 * SLOT_STRIDE] = 0.f; s[14 * SLOT_STRIDE] = 0.f; s[15 * SLOT_STRIDE] = 0.f;
+      }
+    }
   }
 
   if (active) {
+    constexpr int NP = PICK ? 3 : 1;
+#pragma unroll 1
     for (int it = 0; it < PGS_ITERS; ++it) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         if (active & (1u << c)) {
-          const float r0 = ((c & 1) ? H[0] : -H[0]) + ((c & 2) ? H[1] : -H[1]) + ((c & 4) ? H[2] : -H[2]);
-          const float r1 = ((c & 1) ? H[3] : -H[3]) + ((c & 2) ? H[4] : -H[4]) + ((c & 4) ? H[5] : -H[5]);
-          const float r2 = ((c & 1) ? H[6] : -H[6]) + ((c & 2) ? H[7] : -H[7]) + ((c & 4) ? H[8] : -H[8]);
-          table_rows(cb, r0, r1, r2, tb[c], tkn[c], tk1[c], tk2[c], tln[c], tl1[c], tl2[c]);
+          float* s = sm + c * CORNER_WORDS * SLOT_STRIDE;
+          float ln = s[7 * SLOT_STRIDE], l1 = s[8 * SLOT_STRIDE], l2 = s[9 * SLOT_STRIDE];
+          table_rows(v, w, s[0 * SLOT_STRIDE], s[1 * SLOT_STRIDE], s[2 * SLOT_STRIDE], s[3 * SLOT_STRIDE], s[4 * SLOT_STRIDE],
+                     s[5 * SLOT_STRIDE], s[6 * SLOT_STRIDE], ln, l1, l2);
+          s[7 * SLOT_STRIDE] = ln; s[8 * SLOT_STRIDE] = l1; s[9 * SLOT_STRIDE] = l2;
         }
       }
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
         if (active & (1u << (8 + p))) {
-          Contact& k = K[p];
-          row(cb, k.r, k.n, k.bias, 0.0f, 1e30f, k.ln);
-          const float lim = MU * k.ln;
-          row(cb, k.r, k.t1, 0.0f, -lim, lim, k.l1);
-          row(cb, k.r, k.t2, 0.0f, -lim, lim, k.l2);
+          float* s = sm + (8 * CORNER_WORDS + p * PROXY_WORDS) * SLOT_STRIDE;
+          float r[3], n[3], t1[3], t2[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            r[i] = s[(0 + i) * SLOT_STRIDE]; n[i] = s[(3 + i) * SLOT_STRIDE];
+            t1[i] = s[(6 + i) * SLOT_STRIDE]; t2[i] = s[(9 + i) * SLOT_STRIDE];
+          }
+          float ln = s[13 * SLOT_STRIDE], l1 = s[14 * SLOT_STRIDE], l2 = s[15 * SLOT_STRIDE];
+          row(v, w, r, n, s[12 * SLOT_STRIDE], 0.0f, 1e30f, ln);
+          const float lim = MU * ln;
+          row(v, w, r, t1, 0.0f, -lim, lim, l1);
+          row(v, w, r, t2, 0.0f, -lim, lim, l2);
+          s[13 * SLOT_STRIDE] = ln; s[14 * SLOT_STRIDE] = l1; s[15 * SLOT_STRIDE] = l2;
         }
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 3; ++i) cb.pos[i] = fmaf(cb.v[i], DT, cb.pos[i]);
+  for (int i = 0; i < 3; ++i) { cbm.v[i] = v[i]; cbm.w[i] = w[i]; cbm.pos[i] = fmaf(v[i], DT, cb.pos[i]); }
   // quaternion exponential map; half angle = |w| dt / 2 is far inside [-pi/4, pi/4] (|w| < 370 rad/s): polynomials only
-  const float w2 = cb.w[0] * cb.w[0] + cb.w[1] * cb.w[1] + cb.w[2] * cb.w[2];
+  const float w2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   const float h2 = w2 * (0.25f * DT * DT);                   // (half angle)^2
   // sin(h)/|w| = (dt/2) sin(h)/h,  sin(h)/h = 1 - h2/6 + h2^2/120 - h2^3/5040 ;  cos(h) = 1 - h2/2 + h2^2/24 - ...
   const float sinc = fmaf(h2, fmaf(h2, fmaf(h2, -1.9841270e-4f, 8.3333333e-3f), -1.6666667e-1f), 1.0f);
   const float co = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
-  const float s = 0.5f * DT * sinc;
-  const float dq[4] = {cb.w[0] * s, cb.w[1] * s, cb.w[2] * s, co};
+  const float sh = 0.5f * DT * sinc;
+  const float dq[4] = {w[0] * sh, w[1] * sh, w[2] * sh, co};
   const float* q = cb.quat;
   float nq[4] = {dq[3] * q[0] + dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1],
                  dq[3] * q[1] + dq[1] * q[3] + dq[2] * q[0] - dq[0] * q[2],
@@ -307,7 +340,7 @@ static __device__ __noinline__ void step(State& cb, const float (&ee)[3], const 
                  dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2]};
   const float inv = rsqrtf(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) cb.quat[i] = nq[i] * inv;
+  for (int i = 0; i < 4; ++i) cbm.quat[i] = nq[i] * inv;
 }
 
 }  // namespace cube
