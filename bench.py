@@ -343,7 +343,7 @@ def run_ours(args):
     d2h = n * envs[0].obs_dim * 4 + n * 4 + n + n
 
     extra = {}
-    if rank == 0 and not args.quick:
+    if rank == 0 and world == 1 and not args.quick:          # single-GPU secondary numbers; the scaling runs skip them
         extra = side_measurements(torch, pkg, dev, peak_gbs)
     cpu = cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu) else None
 
@@ -432,8 +432,28 @@ def side_measurements(torch, pkg, dev, peak_gbs):
             for e in envs:
                 e.close()
         out["other_configs"] = res
+        # "a second number with the real TD3 actor in the loop (CUDA-graph captured)": one lockstep rollout
+        # step = actor forward + exploration noise + fused env step + replay store + episode statistics, no learning
+        from drl_on_robot_arm_b200 import train
+        tr = train.make_trainer(task="reach", algo="TD3_MLP", n_envs=N_ENVS, device=dev, seed=0, minimal_episodes=10 ** 12,
+                                sync_every=10 ** 9)
+        for _ in range(20):
+            tr.rollout_step()
+        tr._stream.synchronize()
+        k = 1000
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(tr._stream)
+        for _ in range(k):
+            tr.rollout_step()
+        e1.record(tr._stream)
+        tr._stream.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / k
+        out["rollout_with_td3_actor"] = {"env_steps_per_s": N_ENVS / sec, "us_per_rollout_step": sec * 1e6, "n_envs": N_ENVS,
+                                         "what": "CUDA-graph replay of {TD3 actor forward (PyTorch), armsim_explore N(0,0.98) noise, fused reach "
+                                                 "step, trajectory-replay store, armsim_track_episodes} per lockstep step, device-timed"}
+        tr.env.close(); tr.replay.close()
     except Exception as e:  # secondary numbers must never kill the headline line
-        out["other_configs"] = {"error": repr(e)}
+        out.setdefault("other_configs", {})["error"] = repr(e)
     return out
 
 

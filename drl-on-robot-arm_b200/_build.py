@@ -41,6 +41,8 @@ def build_libarmsim(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libarmsim.so (no CPU fallback exists)")
     cus = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
     cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_PATH + ".tmp"] + cus
+    if os.environ.get("ARMSIM_LANE_BLOCK"):          # tuning experiments only (reach: cube scratch assumes 128)
+        cmd.insert(1, "-DARMSIM_LANE_BLOCK=" + os.environ["ARMSIM_LANE_BLOCK"])
     if os.environ.get("ARMSIM_SPARSE_MIN_BLOCKS"):   # tuning experiments only
         cmd.insert(1, "-DARMSIM_SPARSE_MIN_BLOCKS=" + os.environ["ARMSIM_SPARSE_MIN_BLOCKS"])
     if verbose:

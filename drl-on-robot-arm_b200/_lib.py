@@ -14,16 +14,18 @@ ROBOT_KUKA_IIWA, ROBOT_DIANA_S1, ROBOT_CUSTOM = 0, 1, 2
 MODE_IK_TELEPORT, MODE_TORQUE = 0, 1
 MAP_AUTO, MAP_LANE, MAP_WARP = 0, 1, 2
 (F_Q, F_QD, F_GOAL, F_STEP, F_EPISODE, F_CUBE_POS, F_CUBE_QUAT, F_CUBE_LINVEL, F_CUBE_ANGVEL, F_LAST_DIST, F_GRIP,
- F_IK_ITERS) = range(12)
+ F_IK_ITERS, F_EP_RETURN, F_EXPLORE_COUNT) = range(14)
+STATE_FIELDS = tuple(f for f in range(14) if f != F_IK_ITERS)      # everything a checkpoint has to carry
 FIELD_WIDTH = {F_Q: 7, F_QD: 7, F_GOAL: 3, F_STEP: 1, F_EPISODE: 1, F_CUBE_POS: 3, F_CUBE_QUAT: 4, F_CUBE_LINVEL: 3,
-               F_CUBE_ANGVEL: 3, F_LAST_DIST: 1, F_GRIP: 1, F_IK_ITERS: 1}
-INT_FIELDS = (F_STEP, F_EPISODE, F_IK_ITERS)
+               F_CUBE_ANGVEL: 3, F_LAST_DIST: 1, F_GRIP: 1, F_IK_ITERS: 1, F_EP_RETURN: 1, F_EXPLORE_COUNT: 1}
+INT_FIELDS = (F_STEP, F_EPISODE, F_IK_ITERS, F_EXPLORE_COUNT)
 
 EXPORTS = [
     "armsim_abi_version", "armsim_last_error", "armsim_default_config", "armsim_create", "armsim_destroy",
     "armsim_reset", "armsim_step", "armsim_step_host", "armsim_reset_host", "armsim_set_state", "armsim_get_state",
     "armsim_obs_dim", "armsim_action_dim", "armsim_n_envs", "armsim_mapping", "armsim_launch_count", "armsim_fk_host",
     "armsim_host_buffers", "armsim_step_ex", "armsim_step_host_async", "armsim_step_host_wait",
+    "armsim_explore", "armsim_track_episodes", "armsim_episode_stats", "armsim_set_episode_stats",
     "armsim_replay_create", "armsim_replay_destroy", "armsim_replay_begin", "armsim_replay_store", "armsim_replay_sample",
     "armsim_replay_gather", "armsim_replay_info", "armsim_replay_table", "armsim_replay_last_error",
     "armsim_replay_state_bytes", "armsim_replay_get_state", "armsim_replay_set_state",
@@ -91,6 +93,10 @@ def lib():
     L.armsim_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.armsim_step_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.armsim_step_host_async.argtypes = [vp, vp]
+    L.armsim_explore.argtypes = [vp, vp, C.c_float, C.c_float, vp, vp]
+    L.armsim_track_episodes.argtypes = [vp, vp, vp, vp, vp]
+    L.armsim_episode_stats.argtypes = [vp, C.POINTER(C.c_double)]
+    L.armsim_set_episode_stats.argtypes = [vp, C.POINTER(C.c_double)]
     L.armsim_step_host_wait.argtypes = [vp, vp, vp, vp, vp]
     L.armsim_reset_host.argtypes = [vp, vp, vp]
     L.armsim_host_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5

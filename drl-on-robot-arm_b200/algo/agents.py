@@ -27,7 +27,8 @@ class _Learner:
         self.target = copy.deepcopy(self.net)
         for p in self.target.parameters():
             p.requires_grad_(False)
-        self.opt = torch.optim.Adam(self.net.parameters(), lr=lr)
+        # capturable: the step counter lives on the device, so a whole update can be recorded in a CUDA graph (train.py)
+        self.opt = torch.optim.Adam(self.net.parameters(), lr=lr, capturable=torch.device(device).type == "cuda")
         self.bucket = GradBucket(self.net.parameters()) if bucket else None
 
     def step(self, loss):
@@ -53,6 +54,11 @@ class _Learner:
 
 class _AgentBase:
     _nets = ()          # (attribute name, file suffix) pairs written by save()
+
+    def update_cycle(self):
+        """(trains per cycle, phase): the host-side control flow of train() repeats every `cycle` calls and depends only
+        on `phase` -- what a CUDA graph of `cycle` consecutive updates is keyed by (VectorTrainer.train_updates)"""
+        return 1, 0
 
     def __init__(self, state_dim, action_dim, action_bound, hidden_dim, sigma, tau, gamma, device, distributed):
         self.state_dim, self.action_dim, self.action_bound = state_dim, action_dim, action_bound
@@ -169,6 +175,9 @@ class TD3_MLP(_AgentBase):
     def act(self, states):
         return self.actor(states)
 
+    def update_cycle(self):
+        return int(self.policy_freq), self.total_it % int(self.policy_freq)      # delayed actor update, TD3_mlp.py:151
+
     def train(self, transition_dict, sync=True):
         s, a, r, s2, d = self._batch(transition_dict)
         self.total_it += 1
@@ -216,6 +225,9 @@ class DADDPG_MLP(_DoubleActorBase):
 
     def _q_pair(self, states, a1, a2):
         return self.critic(states, a1), self.critic(states, a2)
+
+    def update_cycle(self):
+        return 2, self.total_it % 2                                              # the actors alternate, DADDPG_mlp.py:119
 
     def train(self, transition_dict, batch_size=opt.batch_size, sync=True):
         return self.update(transition_dict, batch_size, sync)

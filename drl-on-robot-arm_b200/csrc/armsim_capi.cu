@@ -43,6 +43,7 @@ struct ArmSim {
   char* h_pin = nullptr;         // mapped + portable pinned block: [actions | obs | reward | done | success | flag]
   char* d_io = nullptr;          // device twin of the same layout (large batches: DMA copies instead of zero-copy)
   size_t off_obs = 0, off_reward = 0, off_done = 0, off_success = 0, out_bytes = 0, act_bytes = 0;
+  unsigned long long* d_stats = nullptr;   // {episodes, successes, return sum (2^-16 fixed point)} of armsim_track_episodes
   unsigned int* d_cta_seq = nullptr;   // per-block launch counters of the doorbells (device)
   volatile unsigned int* h_flags = nullptr;   // per-block doorbells (mapped host memory, tail of h_pin)
   unsigned int seq = 0;                // host-path launches so far == the value every doorbell shows when one is done
@@ -136,7 +137,8 @@ static int field_width(int32_t f) {
     case ARMSIM_F_Q: case ARMSIM_F_QD: return 7;
     case ARMSIM_F_GOAL: case ARMSIM_F_CUBE_POS: case ARMSIM_F_CUBE_LINVEL: case ARMSIM_F_CUBE_ANGVEL: return 3;
     case ARMSIM_F_CUBE_QUAT: return 4;
-    case ARMSIM_F_STEP: case ARMSIM_F_EPISODE: case ARMSIM_F_LAST_DIST: case ARMSIM_F_GRIP: case ARMSIM_F_IK_ITERS: return 1;
+    case ARMSIM_F_STEP: case ARMSIM_F_EPISODE: case ARMSIM_F_LAST_DIST: case ARMSIM_F_GRIP: case ARMSIM_F_IK_ITERS:
+    case ARMSIM_F_EP_RETURN: case ARMSIM_F_EXPLORE_COUNT: return 1;
     default: return -1;
   }
 }
@@ -156,6 +158,8 @@ static void* field_ptr(ArmSim* s, int32_t f) {
     case ARMSIM_F_LAST_DIST: return s->S.last_dist;
     case ARMSIM_F_GRIP: return s->S.grip;
     case ARMSIM_F_IK_ITERS: return s->S.ik_iters;
+    case ARMSIM_F_EP_RETURN: return s->S.ep_return;
+    case ARMSIM_F_EXPLORE_COUNT: return s->S.explore_count;
     default: return nullptr;
   }
 }
@@ -225,6 +229,7 @@ void armsim_destroy(ArmSim* s) {
   if (s->d_io) cudaFree(s->d_io);
   if (s->host_graph) cudaGraphExecDestroy(s->host_graph);
   if (s->d_cta_seq) cudaFree(s->d_cta_seq);
+  if (s->d_stats) cudaFree(s->d_stats);
   if (s->h_pin) cudaFreeHost(s->h_pin);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -361,7 +366,7 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   const size_t n = (size_t)s->n;
   auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t sz_q = pad(7 * n * 4), sz_goal = pad(3 * n * 4), sz_i = pad(n * 4), sz_b = pad(n), sz_cube = pad(13 * n * 4);
-  const size_t total = 2 * sz_q + sz_goal + 3 * sz_i + sz_b + sz_cube + 2 * sz_i;
+  const size_t total = 2 * sz_q + sz_goal + 3 * sz_i + sz_b + sz_cube + 4 * sz_i;
   if (cudaMalloc(&s->state_block, total) != cudaSuccess) {
     cudaGetLastError();
     delete s;
@@ -379,6 +384,8 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   s->S.cube = (float*)b; b += sz_cube;
   s->S.last_dist = (float*)b; b += sz_i;
   s->S.grip = (float*)b; b += sz_i;
+  s->S.ep_return = (float*)b; b += sz_i;
+  s->S.explore_count = (unsigned int*)b; b += sz_i;
 
   // host-path staging
   s->act_bytes = pad(n * s->act_dim * 4);
@@ -393,6 +400,8 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   s->grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
   const size_t flag_bytes = pad((size_t)s->grid * sizeof(unsigned int));
   if (cudaMalloc((void**)&s->d_io, s->act_bytes + s->out_bytes) != cudaSuccess ||
+      cudaMalloc((void**)&s->d_stats, 3 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(s->d_stats, 0, 3 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc((void**)&s->d_cta_seq, flag_bytes) != cudaSuccess ||
       cudaMemset(s->d_cta_seq, 0, flag_bytes) != cudaSuccess ||
       cudaHostAlloc((void**)&s->h_pin, s->act_bytes + s->out_bytes + flag_bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
@@ -552,6 +561,45 @@ int armsim_step_host_wait(ArmSim* s, float* obs_host, float* reward_host, uint8_
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_host_wait: null handle");
   if (!obs_host || !reward_host || !done_host || !success_host) return fail(ARMSIM_E_INVALID, "armsim_step_host_wait: null buffer");
   return host_step_wait(s, obs_host, reward_host, done_host, success_host);
+}
+
+int armsim_explore(ArmSim* s, const float* actor_out_dev, float noise_std, float clip, float* action_out_dev, void* stream) {
+  if (!s || !actor_out_dev || !action_out_dev) return fail(ARMSIM_E_INVALID, "armsim_explore: null argument");
+  if (!(noise_std >= 0.0f)) return fail(ARMSIM_E_INVALID, "armsim_explore: noise_std must be >= 0");
+  explore_kernel<<<s->grid, LANE_BLOCK, 0, (cudaStream_t)stream>>>(s->task, s->S, s->act_dim, actor_out_dev, noise_std, clip, action_out_dev);
+  s->launches += 1;
+  CU(cudaGetLastError());
+  return ARMSIM_OK;
+}
+
+int armsim_track_episodes(ArmSim* s, const float* reward_dev, const uint8_t* done_dev, const uint8_t* success_dev, void* stream) {
+  if (!s || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_track_episodes: null argument");
+  track_episodes_kernel<<<s->grid, LANE_BLOCK, 0, (cudaStream_t)stream>>>(s->n, s->S, reward_dev, done_dev, success_dev, s->d_stats);
+  s->launches += 1;
+  CU(cudaGetLastError());
+  return ARMSIM_OK;
+}
+
+int armsim_episode_stats(ArmSim* s, double out[3]) {
+  if (!s || !out) return fail(ARMSIM_E_INVALID, "armsim_episode_stats: null argument");
+  CU(cudaSetDevice(s->cfg.device));
+  unsigned long long h[3];
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(h, s->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+  out[0] = (double)h[0];
+  out[1] = (double)h[1];
+  out[2] = (double)(long long)h[2] / 65536.0;
+  return ARMSIM_OK;
+}
+
+int armsim_set_episode_stats(ArmSim* s, const double in[3]) {
+  if (!s || !in) return fail(ARMSIM_E_INVALID, "armsim_set_episode_stats: null argument");
+  CU(cudaSetDevice(s->cfg.device));
+  const unsigned long long h[3] = {(unsigned long long)llround(in[0]), (unsigned long long)llround(in[1]),
+                                   (unsigned long long)llround(in[2] * 65536.0)};
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(s->d_stats, h, sizeof(h), cudaMemcpyHostToDevice));
+  return ARMSIM_OK;
 }
 
 int armsim_reset_host(ArmSim* s, const uint8_t* mask_host, float* obs_host) {

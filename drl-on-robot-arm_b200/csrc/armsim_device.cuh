@@ -44,6 +44,8 @@ struct StatePtrs {
   float* cube;       // [13][n] pos3 quat4 v3 w3
   float* last_dist;  // [n]
   float* grip;       // [n]
+  float* ep_return;  // [n]     return of the running episode (armsim_track_episodes)
+  unsigned int* explore_count;  // [n]  exploration-noise draws so far (armsim_explore)
 };
 
 // ------------------------------------------------------------------------------------------------ Philox4x32-10

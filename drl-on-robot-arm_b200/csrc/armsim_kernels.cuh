@@ -10,7 +10,10 @@
 #include "aba_device.cuh"
 #include "cube_model.cuh"
 
-constexpr int LANE_BLOCK = 128;
+#ifndef ARMSIM_LANE_BLOCK
+#define ARMSIM_LANE_BLOCK 128
+#endif
+constexpr int LANE_BLOCK = ARMSIM_LANE_BLOCK;
 // Two builds of the reach-type step kernels: the default one takes the registers it wants (128, no spills: shortest
 // dependent chain; 4 resident blocks per SM, what a single wave needs) and a "dense" one capped at 80 registers for
 // 6 resident blocks per SM (a few spills, but 50% more warps to hide latency with).  Measured on B200, round 1:
@@ -436,6 +439,75 @@ step_torque_kernel(const __grid_constant__ ChainParams C, const __grid_constant_
     }
   }
   notify_host(H);
+}
+
+// ---------------------------------------------------------------------------------------------- rollout bookkeeping
+// main.py:200 (and :116-117 with the clip) for the whole batch: action = actor output + noise_std * N(0,1).
+// One lane per env; Philox4x32-10 counter = (global env id, draws so far of this env, block of 4 normals), key = seed
+// with a domain tag, Box-Muller on the 4 words.
+__global__ void __launch_bounds__(LANE_BLOCK)
+explore_kernel(const __grid_constant__ TaskParams T, const StatePtrs S, int act_dim, const float* __restrict__ actor_out,
+               float noise_std, float clip, float* __restrict__ action_out) {
+  const int e = blockIdx.x * LANE_BLOCK + threadIdx.x;
+  if (e >= T.n) return;
+  const unsigned long long gid = T.gid_offset + (unsigned long long)e;
+  const unsigned int draw = S.explore_count[e];
+  S.explore_count[e] = draw + 1u;
+  for (int k0 = 0; k0 < act_dim; k0 += 4) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), draw, (uint32_t)(k0 >> 2), T.seed_lo ^ 0x4E4F4953u, T.seed_hi, r);
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = ((float)(r[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-08f;     // (0, 1)
+      const float u2 = (float)(r[2 * h + 1] >> 8) * 5.9604644775390625e-08f;           // [0, 1)
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      z[2 * h] = rad * cs;
+      z[2 * h + 1] = rad * sn;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k0 + k < act_dim) {
+        float a = fmaf(noise_std, z[k], actor_out[(size_t)e * act_dim + k0 + k]);
+        if (clip > 0.0f) a = fminf(fmaxf(a, -clip), clip);
+        action_out[(size_t)e * act_dim + k0 + k] = a;
+      }
+    }
+  }
+}
+
+// main.py:202-207, :222-229 for the whole batch: accumulate the running return, fold finished episodes into
+// {episodes, successes, return sum}.  Warp-aggregated; the return sum is an integer (2^-16 fixed point) so the total is
+// independent of the order in which warps arrive.
+__global__ void __launch_bounds__(LANE_BLOCK)
+track_episodes_kernel(int n, const StatePtrs S, const float* __restrict__ reward, const uint8_t* __restrict__ done,
+                      const uint8_t* __restrict__ success, unsigned long long* __restrict__ stats) {
+  const int e = blockIdx.x * LANE_BLOCK + threadIdx.x;
+  const bool live = e < n;
+  bool fin = false, suc = false;
+  long long fx = 0;
+  if (live) {
+    float ret = S.ep_return[e] + reward[e];
+    fin = done[e] != 0;
+    if (fin) {
+      suc = success[e] != 0;
+      fx = llrintf(ret * 65536.0f);
+      ret = 0.0f;
+    }
+    S.ep_return[e] = ret;
+  }
+  const unsigned mf = __ballot_sync(0xffffffffu, fin);
+  if (mf == 0u) return;
+  const unsigned ms = __ballot_sync(0xffffffffu, suc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fx += __shfl_xor_sync(0xffffffffu, fx, o);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(stats + 0, (unsigned long long)__popc(mf));
+    if (ms) atomicAdd(stats + 1, (unsigned long long)__popc(ms));
+    atomicAdd(stats + 2, (unsigned long long)fx);
+  }
 }
 
 template <int TASK>

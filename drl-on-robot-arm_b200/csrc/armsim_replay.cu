@@ -64,7 +64,6 @@ __global__ void __launch_bounds__(RB)
 replay_store_kernel(const ReplayDev D, const float* __restrict__ action, const float* __restrict__ reward,
                     const uint8_t* __restrict__ done, const float* __restrict__ final_obs, const float* __restrict__ obs_out) {
   __shared__ unsigned int s_warp[RB / 32];
-  __shared__ unsigned int s_running;
   __shared__ bool s_last;
   const unsigned long long now = D.counters[0];
   const size_t row = (size_t)(now % (unsigned long long)D.W);
@@ -85,44 +84,53 @@ replay_store_kernel(const ReplayDev D, const float* __restrict__ action, const f
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (threadIdx.x == 0) s_running = 0;
+  // ONE pass: thread t owns the env range [t*chunk, (t+1)*chunk); it counts its commits, the block does a single
+  // exclusive scan over the 256 counts, and each thread then writes its commits to consecutive slots -- env order is
+  // preserved (deterministic table), with two block barriers in total instead of two per 256 envs.
   const unsigned long long base = D.counters[1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c0 = 0; c0 < n; c0 += RB) {
-    const int e = c0 + threadIdx.x;
-    long long s = 0, L = 0;
-    bool commit = false, dn = false;
-    if (e < n) {
-      dn = done[e] != 0;
-      if (dn) {
-        s = D.ep_start[e];
-        L = (long long)now - s + 1;
-        commit = L >= 1 && L < (long long)D.W;       // an episode longer than the ring cannot be replayed
+  const int chunk = (n + RB - 1) / RB;
+  const int lo = min(n, (int)threadIdx.x * chunk), hi = min(n, lo + chunk);
+  unsigned int mine = 0;
+  for (int e = lo; e < hi; ++e) {
+    if (done[e] != 0) {
+      const long long L = (long long)now - D.ep_start[e] + 1;
+      mine += (L >= 1 && L < (long long)D.W) ? 1u : 0u;       // an episode longer than the ring cannot be replayed
+    }
+  }
+  unsigned int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  unsigned int before = incl - mine, total = 0;
+  for (int w = 0; w < RB / 32; ++w) {
+    const unsigned int c = s_warp[w];
+    if (w < warp) before += c;
+    total += c;
+  }
+  {
+    unsigned int k = 0;
+    for (int e = lo; e < hi; ++e) {
+      if (done[e] != 0) {
+        const long long st = D.ep_start[e];
+        const long long L = (long long)now - st + 1;
+        if (L >= 1 && L < (long long)D.W) {
+          const unsigned long long slot = (base + before + k) % (unsigned long long)D.cap;
+          D.t_env[slot] = e;
+          D.t_start[slot] = st;
+          D.t_len[slot] = (int)L;
+          ++k;
+        }
+        D.ep_start[e] = (long long)now + 1;
       }
     }
-    const unsigned int bal = __ballot_sync(0xffffffffu, commit);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    unsigned int before = __popc(bal & ((1u << lane) - 1u)), total = 0;
-    for (int w = 0; w < RB / 32; ++w) {
-      const unsigned int c = s_warp[w];
-      if (w < warp) before += c;
-      total += c;
-    }
-    const unsigned int run = s_running;
-    if (commit) {
-      const unsigned long long slot = (base + run + before) % (unsigned long long)D.cap;
-      D.t_env[slot] = e;
-      D.t_start[slot] = s;
-      D.t_len[slot] = (int)L;
-    }
-    if (dn) D.ep_start[e] = (long long)now + 1;
-    __syncthreads();
-    if (threadIdx.x == 0) s_running = run + total;
-    __syncthreads();
   }
   if (threadIdx.x == 0) {
-    D.counters[1] = base + s_running;
+    D.counters[1] = base + total;
     *D.blocks_done = 0;
     __threadfence();
     D.counters[0] = now + 1;

@@ -119,6 +119,16 @@ class ArmSimHandle:
         call()
         return self._hb[1:]
 
+    def episode_stats(self):
+        """{episodes finished, successes, sum of finished returns} accumulated by track_episodes (float64[3], synchronous)"""
+        out = (C.c_double * 3)()
+        L.check(L.lib().armsim_episode_stats(self.h, out))
+        return np.array(out[:], np.float64)
+
+    def set_episode_stats(self, stats):
+        a = (C.c_double * 3)(*[float(x) for x in stats])
+        L.check(L.lib().armsim_set_episode_stats(self.h, a))
+
     def step_async(self):
         """gym.vector's step_async on the pinned block: actions are read from host_buffers()[0]; returns at once"""
         calls = getattr(self, "_async_calls", None)
@@ -195,6 +205,24 @@ class BatchedArmEnv(ArmSimHandle):
             m = mask.data_ptr()
         L.check(L.lib().armsim_reset(self.h, m, self.obs.data_ptr(), self._stream()))
         return self.obs
+
+    def explore(self, actor_out, noise_std, clip=0.0, out=None):
+        """main.py:200 / :116-117 on the device: out = actor_out + noise_std * N(0,1) (clipped to +-clip when clip > 0);
+        in-kernel Philox noise keyed by (seed, global env id, draws so far), so CUDA-graph replays draw fresh noise"""
+        t = self.torch
+        if actor_out.dtype != t.float32 or not actor_out.is_contiguous():
+            actor_out = actor_out.to(t.float32).contiguous()
+        if out is None:
+            out = t.empty_like(actor_out)
+        L.check(L.lib().armsim_explore(self.h, actor_out.data_ptr(), float(noise_std), float(clip), out.data_ptr(), self._stream()))
+        return out
+
+    def track_episodes(self, reward=None, done=None, success=None):
+        """main.py:202-207, :222-229 on the device: running returns + {episodes, successes, return sum} (episode_stats())"""
+        r = self.reward if reward is None else reward
+        d = self.done if done is None else done
+        s = self.success if success is None else success
+        L.check(L.lib().armsim_track_episodes(self.h, r.data_ptr(), d.data_ptr(), s.data_ptr(), self._stream()))
 
     def step(self, action, out=None, final_obs=None):
         """action: float32 CUDA tensor [N, act_dim].  Returns (obs, reward, done, success) views of the env's own

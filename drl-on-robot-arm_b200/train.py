@@ -23,6 +23,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib as L
 from .config import opt
 from .distributed import allreduce_scalars
 from .metrics import MetricsSink
@@ -31,7 +32,8 @@ from .metrics import MetricsSink
 class VectorTrainer:
     def __init__(self, env, agent, replay, noise_std=None, clip_actions=False, batch_size=None, n_train=None,
                  minimal_episodes=None, use_her=True, her_ratio=None, dis_threshold=0.1, window_episodes=None, avg_window=10,
-                 sync_every=16, metrics=None, save_prefix=None, use_cuda_graph=True, max_updates_per_sync=None):
+                 sync_every=16, metrics=None, save_prefix=None, use_cuda_graph=True, max_updates_per_sync=None,
+                 fused_bookkeeping=True, graph_updates=None):
         self.env, self.agent, self.replay = env, agent, replay
         self.device = env.device
         self.n = env.n
@@ -54,9 +56,13 @@ class VectorTrainer:
         self.save_prefix = save_prefix
         self.use_cuda_graph = bool(use_cuda_graph)
         self.max_updates_per_sync = max_updates_per_sync
+        self.fused_bookkeeping = bool(fused_bookkeeping)       # armsim_explore / armsim_track_episodes vs torch elementwise ops
+        # CUDA-graph the learning updates (single GPU; the multi-GPU path keeps eager updates around its all-reduce)
+        self.graph_updates = (self.world == 1 and self.use_cuda_graph) if graph_updates is None else bool(graph_updates)
+        self._update_graphs, self._eager_updates = {}, 0
         dev = self.device
         # device-side episode statistics: [episodes finished, successes, sum of finished returns]
-        self.stats = torch.zeros(3, device=dev, dtype=torch.float64)
+        self._stats = torch.zeros(3, device=dev, dtype=torch.float64)
         self.ep_return = torch.zeros(self.n, device=dev, dtype=torch.float32)
         self.actions = torch.zeros((self.n, env.act_dim), device=dev)
         self.obs = None
@@ -78,11 +84,20 @@ class VectorTrainer:
             self.obs = self.env.reset()
             self.replay.begin(self.obs)
             self.ep_return.zero_()
+            if self.fused_bookkeeping:
+                self.env.set_state(L.F_EP_RETURN, np.zeros(self.n, np.float32))
         self._stream.synchronize()
 
     def _rollout_body(self):
         env = self.env
         a = self.agent.act(env.obs)
+        if self.fused_bookkeeping:
+            # main.py:200 (+ :117 clip) and :202-207 as two small kernels of the engine instead of ~16 elementwise torch ops
+            env.explore(a, self.noise_std, self.action_bound if self.clip_actions else 0.0, out=self.actions)
+            obs, rew, done, succ = env.step(self.actions, final_obs=True)
+            self.replay.store(self.actions, rew, done, env.final_obs, obs)
+            env.track_episodes(rew, done, succ)
+            return
         a = a + torch.randn_like(a) * self.noise_std                              # main.py:200
         if self.clip_actions:
             a = a.clamp(-self.action_bound, self.action_bound)                    # main.py:117
@@ -92,8 +107,16 @@ class VectorTrainer:
         self.ep_return += rew
         d = done.to(torch.float32)
         fin = torch.stack([d.sum(), succ.to(torch.float32).sum(), (self.ep_return * d).sum()]).to(torch.float64)
-        self.stats += fin
+        self._stats += fin
         self.ep_return *= (1.0 - d)
+
+    @property
+    def stats(self):
+        """[episodes finished, successes, sum of finished returns] so far (float64 tensor on the host side of a sync)"""
+        if self.fused_bookkeeping:
+            self._stream.synchronize()
+            return torch.from_numpy(self.env.episode_stats())
+        return self._stats
 
     def rollout_step(self):
         """one lockstep step of all envs (one CUDA-graph replay once captured)"""
@@ -117,16 +140,46 @@ class VectorTrainer:
 
     # ------------------------------------------------------------------ learning
     def train_updates(self, k):
-        with torch.cuda.stream(self._stream):
-            for _ in range(k):
-                batch = self.replay.sample(self.batch_size, self.use_her, self.dis_threshold, self.her_ratio)
-                self.agent.train(batch, sync=False)
+        """k updates = k x {replay.sample, agent.train}.  On one GPU the updates run as replays of a CUDA graph that
+        holds one control-flow cycle of the agent (TD3: policy_freq = 3 updates, the third with the actor step; DADDPG:
+        2) -- about a hundred small kernels per update leave one launch each instead of one Python call each.  A graph
+        is keyed by the agent's phase and by the sampler arguments (her_ratio decays during a run)."""
+        k = int(k)
         self.updates += k
+        with torch.cuda.stream(self._stream):
+            while k > 0:
+                cyc, phase = self.agent.update_cycle()
+                if not self.graph_updates or k < cyc or self._eager_updates < 3 * cyc:
+                    self._one_update()
+                    self._eager_updates += 1
+                    k -= 1
+                    continue
+                key = (cyc, phase, self.batch_size, self.use_her, self.dis_threshold, self.her_ratio)
+                g = self._update_graphs.get(key)
+                if g is None:
+                    if len(self._update_graphs) >= 64:
+                        self._update_graphs.clear()
+                    self._stream.synchronize()
+                    it0 = self.agent.total_it
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self._stream):
+                        for _ in range(cyc):
+                            self._one_update()
+                    self._update_graphs[key] = (g, self.agent.total_it - it0)
+                    self.agent.total_it = it0                       # capture records, it does not run
+                    g = self._update_graphs[key]
+                g[0].replay()
+                self.agent.total_it += g[1]
+                k -= cyc
+
+    def _one_update(self):
+        batch = self.replay.sample(self.batch_size, self.use_her, self.dis_threshold, self.her_ratio)
+        self.agent.train(batch, sync=False)
 
     def _sync(self):
         """read the device statistics, all-reduce them over ranks, run the updates that became due, log windows"""
         self._stream.synchronize()
-        local = self.stats.cpu().numpy()
+        local = self.stats.cpu().numpy().copy()
         delta = local - self._last_stats
         self._last_stats = local
         if self.world > 1:
@@ -172,8 +225,7 @@ class VectorTrainer:
 
     # ------------------------------------------------------------------ checkpoint / resume
     def state_dict(self, include_replay=True):
-        from . import _lib as L
-        env_state = {f: self.env.get_state(f) for f in range(L.F_IK_ITERS)}
+        env_state = {f: self.env.get_state(f) for f in L.STATE_FIELDS}
         self._stream.synchronize()
         return {"agent": self.agent.state_dict(), "env": env_state, "env_obs": self.env.obs.cpu(),
                 "replay": self.replay.state_blob() if include_replay else None,
@@ -183,6 +235,8 @@ class VectorTrainer:
                 "torch_rng": torch.get_rng_state(), "cuda_rng": torch.cuda.get_rng_state(self.device)}
 
     def load_state_dict(self, sd):
+        self._update_graphs.clear()                 # recorded updates point at the optimizer state being replaced
+        self._eager_updates = 0
         self.agent.load_state_dict(sd["agent"])
         for f, v in sd["env"].items():
             self.env.set_state(f, v)
@@ -190,7 +244,9 @@ class VectorTrainer:
         self.obs = self.env.obs
         if sd["replay"] is not None:
             self.replay.load_state_blob(sd["replay"])
-        self.stats.copy_(sd["stats"].to(self.device))
+        self._stats.copy_(sd["stats"].to(self.device))
+        if self.fused_bookkeeping:
+            self.env.set_episode_stats(sd["stats"].numpy())
         self.ep_return.copy_(sd["ep_return"].to(self.device))
         for k, v in sd["host"].items():
             setattr(self, k, v)

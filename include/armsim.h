@@ -108,7 +108,9 @@ enum {
   ARMSIM_F_LAST_DIST = 9,      /* f32 [n]    previous cube-target distance (push reward) */
   ARMSIM_F_GRIP = 10,          /* f32 [n]    pick: 1 = fingers closed              */
   ARMSIM_F_IK_ITERS = 11,      /* i32 [n]    read-only: DLS iterations used by the last step */
-  ARMSIM_F_COUNT = 12
+  ARMSIM_F_EP_RETURN = 12,     /* f32 [n]    return of the running episode (armsim_track_episodes) */
+  ARMSIM_F_EXPLORE_COUNT = 13, /* i32 [n]    exploration-noise draws so far (Philox counter of armsim_explore) */
+  ARMSIM_F_COUNT = 14
 };
 
 /* Fill *cfg with the reference constants for `task` (robot kuka_iiwa, IK-teleport mode, n_envs = 1). */
@@ -162,6 +164,24 @@ int armsim_step_host_wait(ArmSim* sim, float* obs_host, float* reward_host, uint
  * copy-free on the host: for n_envs <= 65536 the kernel reads the actions from and writes the results to this block
  * over PCIe itself and rings a doorbell in it (no DMA launches, no stream synchronise).  Any pointer may be NULL. */
 int armsim_host_buffers(ArmSim* sim, float** action, float** obs, float** reward, uint8_t** done, uint8_t** success);
+
+/* Rollout bookkeeping of the reference's train loops, on the device (no counterpart kernel in the reference: these are
+ * the numpy lines around env.step in main.py).
+ *
+ * armsim_explore:  action_out = actor_out + noise_std * N(0,1), clipped to [-clip, clip] when clip > 0
+ *   (main.py:200 `action + np.random.normal(0, action_bound * opt.gamma)`; main.py:116-117 adds the clip).  Normal draws
+ *   come from Philox4x32-10 keyed by the handle's seed with counter (GLOBAL env id, per-env draw count), so a CUDA-graph
+ *   replay draws fresh noise every time and the stream does not depend on how envs are sharded over ranks.
+ *   actor_out_dev, action_out_dev: f32 [n, action_dim]; may alias.
+ * armsim_track_episodes:  episode_return += reward; every env with done != 0 adds {1, success != 0, episode_return} to the
+ *   handle's statistics and restarts its return (main.py:202-207 `episode_return += reward`, :203,:222-229 success-rate
+ *   bookkeeping).  The return sum is kept in 2^-16 fixed point so it does not depend on the order of the atomics.
+ * armsim_episode_stats / armsim_set_episode_stats:  {episodes finished, successes, sum of finished returns}; synchronous. */
+int armsim_explore(ArmSim* sim, const float* actor_out_dev, float noise_std, float clip, float* action_out_dev, void* stream);
+int armsim_track_episodes(ArmSim* sim, const float* reward_dev, const uint8_t* done_dev, const uint8_t* success_dev,
+                          void* stream);
+int armsim_episode_stats(ArmSim* sim, double out[3]);
+int armsim_set_episode_stats(ArmSim* sim, const double in[3]);
 
 /* Inject / read back per-env state (parity tests inject q, goal, cube pose; SURVEY 5 "seeding facts").
  * `bytes` must equal n_envs * width * 4.  Synchronous. */

@@ -52,6 +52,109 @@ def test_trainer_runs_the_reference_cadence(pkg, torch_cuda, tmp_path, algo, tas
     tr.env.close(); tr.replay.close()
 
 
+def test_explore_noise_kernel(pkg, torch_cuda):
+    """armsim_explore (main.py:200, :116-117): exact pass-through at sigma = 0, N(0, sigma) otherwise, fresh draws on every
+    call (also from a CUDA-graph replay), clip honoured, and a noise stream keyed by the GLOBAL env id (shard-invariant)"""
+    torch = torch_cuda
+    n = 65536
+    env = pkg.BatchedArmEnv("reach", n_envs=n, device="cuda:0", seed=5)
+    mu = torch.rand((n, 3), device="cuda") - 0.5
+    assert torch.equal(env.explore(mu, 0.0), mu)
+    a1 = env.explore(mu, 0.98)
+    a2 = env.explore(mu, 0.98)
+    z = ((a1 - mu) / 0.98).double().cpu().numpy().ravel()
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    assert abs((z ** 4).mean() - 3.0) < 0.1 and abs((z ** 3).mean()) < 0.05          # normal: kurtosis 3, no skew
+    assert abs(np.corrcoef(z[0::3], z[1::3])[0, 1]) < 0.01                           # components independent
+    assert not torch.equal(a1, a2)
+    assert abs(np.corrcoef(z, ((a2 - mu) / 0.98).double().cpu().numpy().ravel())[0, 1]) < 0.01
+    c = env.explore(mu, 5.0, clip=0.7)
+    assert float(c.abs().max()) <= 0.7 and float((c.abs() == 0.7).float().mean()) > 0.5
+    # graph replay: the draw counter lives on the device, so every replay is a new draw
+    out = torch.empty_like(mu)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        env.explore(mu, 1.0, out=out)
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            env.explore(mu, 1.0, out=out)
+        g.replay(); st.synchronize(); r1 = out.clone()
+        g.replay(); st.synchronize(); r2 = out.clone()
+    assert not torch.equal(r1, r2)
+    # shard invariance: envs [n/2, n) of this handle == a handle created with env_id_offset = n/2 (same draw count)
+    lo = pkg.BatchedArmEnv("reach", n_envs=n // 2, device="cuda:0", seed=5, env_id_offset=n // 2)
+    whole = pkg.BatchedArmEnv("reach", n_envs=n, device="cuda:0", seed=5)
+    assert torch.equal(whole.explore(mu, 1.0)[n // 2:], lo.explore(mu[n // 2:].contiguous(), 1.0))
+    for e in (env, lo, whole):
+        e.close()
+
+
+def test_track_episodes_matches_host_bookkeeping(pkg, torch_cuda):
+    """armsim_track_episodes (main.py:202-207, :222-229) against the same bookkeeping done in numpy float64"""
+    torch = torch_cuda
+    n = 1000
+    env = pkg.BatchedArmEnv("reach", n_envs=n, device="cuda:0", seed=2, auto_reset=True, max_steps=17, reach_dis=0.05)
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    ret = np.zeros(n); want = np.zeros(3)
+    for k in range(120):
+        a = (torch.rand((n, 3), device="cuda", generator=gen) * 2 - 1) * 0.7
+        obs, rew, done, succ = env.step(a)
+        env.track_episodes()
+        r, d, s = rew.double().cpu().numpy(), done.cpu().numpy().astype(bool), succ.cpu().numpy().astype(bool)
+        ret += r
+        want += [d.sum(), (d & s).sum(), ret[d].sum()]
+        ret[d] = 0.0
+    got = env.episode_stats()
+    assert got[0] == want[0] and got[1] == want[1] and got[0] >= 6 * n
+    assert abs(got[2] - want[2]) <= 1e-4 * got[0]                  # 2^-16 fixed point + f32 running returns
+    assert np.allclose(env.get_state(pkg._lib.F_EP_RETURN), ret, atol=1e-3)
+    env.set_episode_stats([3, 1, -2.5])
+    assert list(env.episode_stats()) == [3.0, 1.0, -2.5]
+    env.close()
+
+
+def test_fused_and_torch_bookkeeping_agree(pkg, torch_cuda):
+    """VectorTrainer with the engine's explore / track_episodes kernels == the same loop in elementwise torch ops when
+    the exploration noise is off (the two paths draw their noise from different generators)"""
+    torch = torch_cuda
+    res = []
+    for fused in (True, False):
+        tr = _mk(pkg, n=200, minimal_episodes=10 ** 9, noise_std=0.0, fused_bookkeeping=fused)
+        tr.env.close()
+        from drl_on_robot_arm_b200.distributed import make_sharded_env
+        tr.env = make_sharded_env("reach", 200, device="cuda:0", seed=3, auto_reset=True, max_steps=12)
+        tr.run(60)
+        res.append((tr.env.get_state(0).copy(), tr.stats.cpu().numpy().copy(), tr.replay.info()))
+        tr.env.close(); tr.replay.close()
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][2] == res[1][2]
+    assert np.array_equal(res[0][1][:2], res[1][1][:2]) and res[0][1][0] >= 200 * 4
+    assert abs(res[0][1][2] - res[1][1][2]) <= 1e-4 * res[0][1][0]
+
+
+@pytest.mark.parametrize("algo", ["DDPG_MLP", "DADDPG_MLP"])
+def test_graphed_updates_equal_eager_updates(pkg, torch_cuda, algo):
+    """train_updates as CUDA-graph replays of one control-flow cycle == the same updates issued one by one (agents without
+    random draws in train(): bit-identical weights, targets and update counters)"""
+    torch = torch_cuda
+    res = []
+    for graphed in (True, False):
+        tr = _mk(pkg, n=128, algo=algo, noise_std=0.3, graph_updates=graphed)
+        tr.env.close()
+        from drl_on_robot_arm_b200.distributed import make_sharded_env
+        tr.env = make_sharded_env("reach", 128, device="cuda:0", seed=3, auto_reset=True, max_steps=10)
+        tr.run(120)
+        assert tr.updates >= 200
+        assert bool(tr._update_graphs) == graphed
+        res.append(([p.detach().clone() for l, _ in tr.agent._learners() for p in list(l.net.parameters()) + list(l.target.parameters())],
+                    tr.updates, tr.agent.total_it))
+        tr.env.close(); tr.replay.close()
+    assert res[0][1:] == res[1][1:]
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+
+
 def test_graph_and_eager_rollouts_agree(pkg, torch_cuda):
     """the CUDA-graph replay of the rollout step does exactly what the eager step does (no learning: pure rollout)"""
     torch = torch_cuda
