@@ -122,8 +122,8 @@ def lib():
     L.armsim_replay_state_bytes.restype = C.c_int64
     L.armsim_replay_get_state.argtypes = [vp, vp, C.c_int64]
     L.armsim_replay_set_state.argtypes = [vp, vp, C.c_int64]
-    if L.armsim_abi_version() != 2:
-        raise ArmsimError("libarmsim ABI version %d != 2" % L.armsim_abi_version())
+    if L.armsim_abi_version() != 3:
+        raise ArmsimError("libarmsim ABI version %d != 3" % L.armsim_abi_version())
     _lib = L
     return L
 

@@ -147,10 +147,11 @@ __device__ __forceinline__ float gripper_distance(const State& cb, const float (
 }
 
 // ---- per-thread contact slots in shared memory ---------------------------------------------------------------------
-// Every contact of the oracle's list has a STATIC slot -- 8 corner slots + 3 proxy slots with an "active" bit -- in a
-// per-thread column of dynamic shared memory: word k of the calling thread is scratch[k * SLOT_STRIDE + threadIdx.x]
-// (conflict-free: a warp reads 32 consecutive words).  Offsets are compile-time constants after unrolling, so a
-// sweep is LDS/STS with immediate offsets + a handful of FMAs per row; the cube's velocity state stays in registers.
+// The contacts of the oracle's list live in a per-thread column of dynamic shared memory: word k of the calling thread
+// is scratch[k * SLOT_STRIDE + threadIdx.x] (conflict-free: a warp reads 32 consecutive words).  Corner / table
+// contacts are compacted per lane into slots 0..nc-1 (corner order = the oracle's Gauss-Seidel order), the up to 3
+// arm-proxy contacts have static slots with an "active" bit.  A sweep is LDS/STS + a handful of FMAs per row; the
+// cube's velocity state stays in registers.
 // (Round 1 history: a compacted, dynamically indexed contact array lived in local memory, ~170 instructions per
 // contact per sweep; static slots in registers made ptxas rematerialise the corner geometry inside the sweep loop,
 // ~70-85; the shared-memory slots are ~50 and cut the kernel from 223 to ~120 registers.)
@@ -238,7 +239,8 @@ static __device__ __noinline__ void step(State& cbm, const float (&ee)[3], const
   float* const sm = cube_scratch + threadIdx.x;
   float R[9];
   rot(cb.quat, R);
-  unsigned active = 0u;
+  unsigned active = 0u;               // bits 8.. : arm-proxy slots in contact
+  int nc = 0;                         // corner contacts, compacted in corner order into slots 0 .. nc-1
   {
     float H[9];                      // half-edge vectors: column k of R times HALF
 #pragma unroll
@@ -251,8 +253,8 @@ static __device__ __noinline__ void step(State& cbm, const float (&ee)[3], const
         r[i] = ((c & 1) ? H[3 * i] : -H[3 * i]) + ((c & 2) ? H[3 * i + 1] : -H[3 * i + 1]) + ((c & 4) ? H[3 * i + 2] : -H[3 * i + 2]);
       const float gap = cb.pos[2] + r[2] - TABLE_Z;
       if (gap < MARGIN) {
-        active |= 1u << c;
-        float* s = sm + c * CORNER_WORDS * SLOT_STRIDE;
+        float* s = sm + nc * (CORNER_WORDS * SLOT_STRIDE);
+        ++nc;
         const float a = r[0] * r[0], b = r[1] * r[1], d = r[2] * r[2];
         s[0 * SLOT_STRIDE] = r[0]; s[1 * SLOT_STRIDE] = r[1]; s[2 * SLOT_STRIDE] = r[2];
         s[3 * SLOT_STRIDE] = gap < 0.f ? -ERP * gap * INV_DT : -gap * INV_DT;
@@ -289,19 +291,19 @@ static __device__ __noinline__ void step(State& cbm, const float (&ee)[3], const
     }
   }
 
-  if (active) {
+  if (active | (unsigned)nc) {
     constexpr int NP = PICK ? 3 : 1;
 #pragma unroll 1
     for (int it = 0; it < PGS_ITERS; ++it) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (active & (1u << c)) {
-          float* s = sm + c * CORNER_WORDS * SLOT_STRIDE;
-          float ln = s[7 * SLOT_STRIDE], l1 = s[8 * SLOT_STRIDE], l2 = s[9 * SLOT_STRIDE];
-          table_rows(v, w, s[0 * SLOT_STRIDE], s[1 * SLOT_STRIDE], s[2 * SLOT_STRIDE], s[3 * SLOT_STRIDE], s[4 * SLOT_STRIDE],
-                     s[5 * SLOT_STRIDE], s[6 * SLOT_STRIDE], ln, l1, l2);
-          s[7 * SLOT_STRIDE] = ln; s[8 * SLOT_STRIDE] = l1; s[9 * SLOT_STRIDE] = l2;
-        }
+      // corner slots are compacted per lane, so a warp runs max(nc) bodies (4 for cubes lying flat) instead of one
+      // body per corner any of its lanes touches the table with (up to 8 once some cubes have been tipped over)
+#pragma unroll 1
+      for (int j = 0; j < nc; ++j) {
+        float* s = sm + j * (CORNER_WORDS * SLOT_STRIDE);
+        float ln = s[7 * SLOT_STRIDE], l1 = s[8 * SLOT_STRIDE], l2 = s[9 * SLOT_STRIDE];
+        table_rows(v, w, s[0 * SLOT_STRIDE], s[1 * SLOT_STRIDE], s[2 * SLOT_STRIDE], s[3 * SLOT_STRIDE], s[4 * SLOT_STRIDE],
+                   s[5 * SLOT_STRIDE], s[6 * SLOT_STRIDE], ln, l1, l2);
+        s[7 * SLOT_STRIDE] = ln; s[8 * SLOT_STRIDE] = l1; s[9 * SLOT_STRIDE] = l2;
       }
 #pragma unroll
       for (int p = 0; p < NP; ++p) {

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ARMSIM_ABI_VERSION 2
+#define ARMSIM_ABI_VERSION 3
 #define ARMSIM_NJ 7            /* arm joints (Kuka iiwa, DianaS1) */
 #define ARMSIM_ACT_DIM 3       /* Cartesian EE servo action, reference envs' action_space */
 #define ARMSIM_TORQUE_DIM 7    /* torque mode action */
