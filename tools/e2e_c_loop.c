@@ -35,6 +35,18 @@ int main(int argc, char** argv) {
   double dt = now() - t0;
   printf("{\"n_envs\": %d, \"steps\": %d, \"us_per_step\": %.3f, \"env_steps_per_s\": %.4g, \"check\": %.3f}\n", n, steps,
          1e6 * dt / steps, n * (double)steps / dt, acc);
+  /* with host "think time" between steps (a policy running on the CPU): time spent INSIDE the step call only */
+  for (int think_us = 5; think_us <= 80; think_us *= 2) {
+    double in_call = 0;
+    for (int k = 0; k < steps; ++k) {
+      double t1 = now();
+      step(sim, a, o, r, d, s);
+      double t2 = now();
+      in_call += t2 - t1;
+      while (now() - t2 < 1e-6 * think_us) { }
+    }
+    printf("{\"think_us\": %d, \"us_in_step_call\": %.3f}\n", think_us, 1e6 * in_call / steps);
+  }
   /* staged variant: ordinary (pageable) buffers */
   float* a2 = malloc(n * 3 * 4); float* o2 = malloc(n * 6 * 4); float* r2 = malloc(n * 4); uint8_t* d2 = malloc(n); uint8_t* s2 = malloc(n);
   memcpy(a2, a, n * 3 * 4);
