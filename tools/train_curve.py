@@ -11,7 +11,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import drl_on_robot_arm_b200 as pkg  # noqa: F401
+from drl_on_robot_arm_b200 import distributed as D
 from drl_on_robot_arm_b200 import metrics, train
+
+# torchrun --nproc-per-node G tools/train_curve.py ... : n_envs is PER GPU (BASELINE config 5 = 8 x 4096, DARC)
+rank, world, local = D.init_from_env("nccl")
 
 task = sys.argv[1] if len(sys.argv) > 1 else "reach"
 algo = sys.argv[2] if len(sys.argv) > 2 else "TD3_MLP"
@@ -20,9 +24,16 @@ episode_times = int(sys.argv[4]) if len(sys.argv) > 4 else 100
 out = sys.argv[5] if len(sys.argv) > 5 else None
 budget_s = float(os.environ.get("TRAIN_BUDGET_S", "600"))
 
+t_init = time.time()
+if world > 1:   # first collective = communicator set-up (seconds with 8 ranks): keep it out of the training clock
+    w = torch.ones(1, device="cuda:%d" % local)
+    torch.distributed.all_reduce(w)
+    torch.cuda.synchronize()
+    if rank == 0:
+        print(json.dumps({"nccl_first_collective_s": time.time() - t_init}), flush=True)
 sink = metrics.MetricsSink()
-tr = train.make_trainer(task=task, algo=algo, n_envs=n, device="cuda:0", seed=0, window=1024, metrics=sink, sync_every=32,
-                        window_episodes=5 * n, clip_actions=(os.environ.get("CLIP", "0") == "1"),
+tr = train.make_trainer(task=task, algo=algo, n_envs=n, device="cuda:%d" % local, seed=0, window=1024, metrics=sink, sync_every=32,
+                        window_episodes=5 * n * world, clip_actions=(os.environ.get("CLIP", "0") == "1"),
                         noise_std=float(os.environ["NOISE"]) if "NOISE" in os.environ else None)
 t0 = time.time()
 chunk = 501
@@ -33,13 +44,20 @@ for k in range(episode_times):
     el = time.time() - t0
     log.append({"episode_time": k + 1, "wall_s": el, "env_steps": res["env_steps"], "updates": res["updates"],
                 "success_rate": res["success_rate"], "avg_return": res["avg_return"], "her_ratio": res["her_ratio"]})
-    if (k + 1) % 5 == 0 or k == 0:
+    if rank == 0 and ((k + 1) % 5 == 0 or k == 0):
         print(json.dumps(log[-1]), flush=True)
-    if el > budget_s:
+    stop = torch.tensor([1.0 if el > budget_s else 0.0], device="cuda:%d" % local)
+    if world > 1:
+        torch.distributed.all_reduce(stop, op=torch.distributed.ReduceOp.MAX)      # every rank leaves together
+    if float(stop) > 0:
         break
-summary = {"task": task, "algo": algo, "n_envs": n, "episode_times": len(log), "wall_s": time.time() - t0,
+summary = {"task": task, "algo": algo, "n_envs": n, "n_gpus": world, "n_envs_total": n * world, "episode_times": len(log), "wall_s": time.time() - t0,
            "env_steps_per_s_incl_learning": log[-1]["env_steps"] / (time.time() - t0),
            "success_rate_series": sink.series.get("success_rate", []), "log": log}
-print(json.dumps({k: v for k, v in summary.items() if k != "log"}))
-if out:
-    json.dump(summary, open(out, "w"), indent=1)
+if rank == 0:
+    print(json.dumps({k: v for k, v in summary.items() if k != "log"}))
+    if out:
+        json.dump(summary, open(out, "w"), indent=1)
+if world > 1:
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
