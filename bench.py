@@ -10,9 +10,15 @@ N = 8 is configs[4], 32768 envs sharded 8 x 4096; no data-path collective, SURVE
 
 Timing hygiene: the 4096-env working set (0.5 MB) would sit in L2, so the bench keeps a POOL of independent
 4096-env batches whose touched state exceeds 2x the 126 MB L2 and steps them round-robin: every launch reads and
-writes HBM-cold state.  `value` is device-timed (CUDA events on the launching stream around a CUDA-graph replay of
-exactly K launches, max over ranks); `e2e` is the same metric through the host-buffer C-ABI call
-(armsim_step_host: pinned H2D of the actions, launch, D2H of obs/reward/done/success, every step).
+writes HBM-cold state.  Actions: a ring of 61 independent U(-0.7,0.7) sets (coprime with the pool size), so every env
+sees a different action on each of its steps and random-walks through the workspace like under an untrained policy
+(a constant action per env would pin the arms in workspace corners).  `value` is device-timed (CUDA events on the
+launching stream around a CUDA-graph replay of exactly K launches, after ~0.3 s of untimed replays that bring the
+clocks up and the envs into mid-episode states; max over ranks); `e2e` is the same metric through the host-buffer
+C-ABI call (armsim_step_host on the handle's pinned block: the kernel reads the actions from / writes the results
+to host memory over PCIe every step, the host polls per-block doorbells), timed on the host clock.
+Secondary numbers on the same JSON line (single GPU only): other_configs (push / pick / large-N reach, measured the
+same way), rollout_with_td3_actor, e2e.pipelined_depth2 (step_async / step_wait over two env groups).
 """
 import argparse
 import json
