@@ -34,7 +34,10 @@ if ROOT not in sys.path:
 import numpy as np
 
 N_ENVS = 4096
-ALGO_BYTES = {"reach": 118, "push": 242, "pick": 250, "kuka_reach": 106}    # SURVEY 8(d), per env-step
+ALGO_BYTES = {"reach": 118, "push": 242, "pick": 250, "kuka_reach": 106,     # SURVEY 8(d), per env-step
+              # torque mode (north star's articulated-body step): reads tau 28 + q 28 + qd 28 + goal 12 + step 4,
+              # writes q 28 + qd 28 + step 4 + obs [ee, goal, q, qd] 80 + reward 4 + done 1 + success 1
+              "reach_torque": 246}
 L2_BYTES = 126 * 1024 * 1024
 N_ACT = 61                                                                   # action sets in rotation (prime)
 METRIC = "env-steps/sec (reach, N_envs=4096)"
@@ -399,18 +402,22 @@ def side_measurements(torch, pkg, dev, peak_gbs):
         res = {}
         stream = torch.cuda.Stream(device=dev)
         for task, n in (("reach", 1 << 20), ("reach", 1 << 22), ("push", N_ENVS), ("pick", 2048), ("reach", 32768),
-                        ("push", 1 << 20), ("pick", 1 << 20)):
+                        ("push", 1 << 20), ("pick", 1 << 20), ("reach_torque", N_ENVS), ("reach_torque", 1 << 20)):
+            torque = task.endswith("_torque")
             pool = max(1, int(np.ceil(2.0 * L2_BYTES / (ALGO_BYTES[task] * n))))
             k = 20 * pool if n >= (1 << 20) else 600
-            envs = [pkg.BatchedArmEnv(task, n_envs=n, device=dev, seed=0, auto_reset=True, env_id_offset=b * n)
-                    for b in range(pool)]
+            envs = [pkg.BatchedArmEnv(task.split("_")[0], n_envs=n, device=dev, seed=0, auto_reset=True, env_id_offset=b * n,
+                                      mode="torque" if torque else "ik_teleport") for b in range(pool)]
             na = 7 if n >= (1 << 20) else N_ACT
             if pool % na == 0:
                 na -= 1                                          # keep the ring out of step with the pool
             k = max(na, k // na * na)                            # whole turns of the action ring per replay
-            a = (torch.rand((na, n, 3), device=dev) * 1.4 - 0.7)
-            if task != "reach":
-                a *= 0.4 / 0.7                                  # action_bound 0.4 for push / pick (main.py:457,526)
+            if torque:
+                a = (torch.rand((na, n, 7), device=dev) * 2.0 - 1.0) * 30.0      # joint torques, N m (effort limit 300)
+            else:
+                a = (torch.rand((na, n, 3), device=dev) * 1.4 - 0.7)
+                if task != "reach":
+                    a *= 0.4 / 0.7                              # action_bound 0.4 for push / pick (main.py:457,526)
             with torch.cuda.stream(stream):
                 for j in range(max(3, min(pool, 8))):
                     envs[j % pool].step(a[j % na])
