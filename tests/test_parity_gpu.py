@@ -504,6 +504,32 @@ def test_auto_reset_full_size(pkg, torch_cuda):
     env.close()
 
 
+@pytest.mark.parametrize("task,n_total,shard", [("reach", 32768, 4096), ("reach", 131072, 4096), ("push", 65536, 4096)])
+def test_full_size_equals_its_shards(pkg, torch_cuda, task, n_total, shard):
+    """BASELINE config 5 shape (32768 = 8 x 4096) and sizes that take the dense (register-capped, multi-wave) build of
+    the step kernel: ONE handle over all envs gives bit for bit what the 4096-env shards (single-wave build, Philox
+    keyed by the global env id) give -- results depend neither on the sharding nor on which build ran"""
+    torch = torch_cuda
+    g = torch.Generator(device="cuda").manual_seed(7)
+    sc = 0.7 if task == "reach" else 0.4
+    whole = pkg.BatchedArmEnv(task, n_envs=n_total, seed=4, auto_reset=True, device="cuda:0", max_steps=6)
+    parts = [pkg.BatchedArmEnv(task, n_envs=shard, seed=4, auto_reset=True, device="cuda:0", max_steps=6, env_id_offset=o)
+             for o in range(0, n_total, shard)]
+    assert torch.equal(whole.reset(), torch.cat([p.reset() for p in parts]))
+    n_done = 0
+    for k in range(9):                                             # crosses one timeout + in-kernel auto-reset
+        a = (torch.rand((n_total, 3), device="cuda", generator=g) * 2 - 1) * sc
+        o, r, d, s = whole.step(a)
+        po, pr, pd, ps = zip(*[tuple(t.clone() for t in p.step(a[i * shard:(i + 1) * shard].contiguous())) for i, p in enumerate(parts)])
+        assert torch.equal(o, torch.cat(po)) and torch.equal(r, torch.cat(pr))
+        assert torch.equal(d, torch.cat(pd)) and torch.equal(s, torch.cat(ps))
+        n_done += int(d.sum())
+    assert n_done >= n_total                                       # every env timed out (step 7) and was re-seeded in the kernel
+    whole.close()
+    for p in parts:
+        p.close()
+
+
 @pytest.mark.parametrize("name,odim,dtype", [("RLReachEnv", 6, np.float32), ("RLPushEnv", 9, np.float64),
                                               ("RLPickEnv", 9, np.float64), ("KukaReachEnv", 3, np.float32)])
 def test_drop_in_env_classes(pkg, torch_cuda, name, odim, dtype):
