@@ -198,6 +198,7 @@ class VectorTrainer:
             k = int(self.update_credit * self.n_train)
             if self.max_updates_per_sync is not None:
                 k = min(k, int(self.max_updates_per_sync))
+            k -= k % self.agent.update_cycle()[0]          # whole control-flow cycles (= graph replays); the rest stays credited
             if k > 0:
                 self.update_credit -= k / float(self.n_train)
                 self.train_updates(k)
