@@ -58,7 +58,10 @@ class VectorTrainer:
         self.max_updates_per_sync = max_updates_per_sync
         self.fused_bookkeeping = bool(fused_bookkeeping)       # armsim_explore / armsim_track_episodes vs torch elementwise ops
         # CUDA-graph the learning updates (single GPU; the multi-GPU path keeps eager updates around its all-reduce)
-        self.graph_updates = (self.world == 1 and self.use_cuda_graph) if graph_updates is None else bool(graph_updates)
+        if graph_updates is None:
+            # multi-GPU: EXPERIMENTAL opt-in (the all-reduce is recorded too); one of two 2-GPU trials hung, see DESIGN.md 6
+            graph_updates = self.use_cuda_graph and (self.world == 1 or os.environ.get("ARMSIM_GRAPH_NCCL_UPDATES") == "1")
+        self.graph_updates = bool(graph_updates)
         self._update_graphs, self._eager_updates = {}, 0
         dev = self.device
         # device-side episode statistics: [episodes finished, successes, sum of finished returns]
