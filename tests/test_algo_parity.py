@@ -72,3 +72,26 @@ def test_registry_lookup_like_main_py(pkg):
     from drl_on_robot_arm_b200.config import opt
     agent = getattr(algo, opt.algo)(state_dim=6, action_dim=3, action_bound=0.7, device="cpu")     # main.py:95
     assert type(agent).__name__ == "DADDPG_MLP" and agent.take_action(np.zeros(6, np.float32)).shape == (3,)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_update_cycle_describes_the_host_control_flow(pkg, name):
+    """update_cycle() = (trains per control-flow cycle, phase): which networks a train() call steps depends only on the
+    phase, and repeats every `cycle` calls -- what VectorTrainer keys its CUDA graphs of the updates by"""
+    from drl_on_robot_arm_b200 import algo
+    torch.manual_seed(0)
+    agent = getattr(algo, name)(state_dim=6, action_dim=3, action_bound=0.7, hidden_dim=8, device="cpu")
+    batch = {"states": np.random.rand(16, 6).astype(np.float32), "actions": np.random.rand(16, 3).astype(np.float32),
+             "rewards": np.random.rand(16).astype(np.float32), "next_states": np.random.rand(16, 6).astype(np.float32),
+             "dones": np.zeros(16, np.float32)}
+    cycle, phase0 = agent.update_cycle()
+    assert cycle == {"TD3_MLP": 3, "DADDPG_MLP": 2}.get(name, 1) and phase0 == 0
+    pattern = {}
+    for k in range(3 * cycle):
+        _, phase = agent.update_cycle()
+        before = [[p.detach().clone() for p in l.net.parameters()] for l, _ in agent._learners()]
+        agent.train({kk: vv.copy() for kk, vv in batch.items()})
+        stepped = tuple(any(not torch.equal(a, b) for a, b in zip(bf, l.net.parameters()))
+                        for bf, (l, _) in zip(before, agent._learners()))
+        assert pattern.setdefault(phase, stepped) == stepped          # same phase -> same networks stepped
+    assert len(pattern) == cycle
