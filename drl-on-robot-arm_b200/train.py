@@ -174,6 +174,10 @@ class VectorTrainer:
                 g[0].replay()
                 self.agent.total_it += g[1]
                 k -= cyc
+            if self.world > 1 and self.graph_updates:
+                # a recorded all-reduce runs on THIS stream, eager collectives on the process group's own one: never leave
+                # a replay in flight where the caller may issue another collective (NCCL needs one order on every rank)
+                self._stream.synchronize()
 
     def _one_update(self):
         batch = self.replay.sample(self.batch_size, self.use_her, self.dis_threshold, self.her_ratio)
