@@ -12,11 +12,15 @@ Timing hygiene: the 4096-env working set (0.5 MB) would sit in L2, so the bench 
 4096-env batches whose touched state exceeds 2x the 126 MB L2 and steps them round-robin: every launch reads and
 writes HBM-cold state.  Actions: a ring of 61 independent U(-0.7,0.7) sets (coprime with the pool size), so every env
 sees a different action on each of its steps and random-walks through the workspace like under an untrained policy
-(a constant action per env would pin the arms in workspace corners).  `value` is device-timed (CUDA events on the
-launching stream around a CUDA-graph replay of exactly K launches, after ~0.3 s of untimed replays that bring the
-clocks up and the envs into mid-episode states; max over ranks); `e2e` is the same metric through the host-buffer
-C-ABI call (armsim_step_host on the handle's pinned block: the kernel reads the actions from / writes the results
-to host memory over PCIe every step, the host polls per-block doorbells), timed on the host clock.
+(a constant action per env would pin the arms in workspace corners).  The pool is walked INDEPENDENTLY of K: the
+K-launch unit is captured as ceil(pool / K) CUDA graphs that together cover the whole pool, replayed round-robin, so
+consecutive replays never touch the same batches whatever K the caller picks (K = 20 and K = 2000 measure the same
+thing).  `value` is device-timed: after ~0.3 s of untimed replays (clocks up, envs in mid-episode states) R >= 50
+replays are each bracketed by a CUDA event pair on the launching stream, the whole set bracketed by a barrier +
+synchronize; per rank the MEDIAN replay time counts (p10 / p90 are printed too), max over ranks.  `e2e` is the same
+metric through the host-buffer C-ABI call (armsim_step_host on the handle's pinned block: the kernel reads the actions
+from / writes the results to host memory over PCIe every step, the host polls per-block doorbells), timed on the host
+clock as R repeats of a K-step loop, median.
 Secondary numbers on the same JSON line (single GPU only): other_configs (push / pick / large-N reach, measured the
 same way), rollout_with_td3_actor, e2e.pipelined_depth2 (step_async / step_wait over two env groups).
 """
@@ -46,9 +50,12 @@ UNIT = "env-steps/s"
 
 def load_traffic(task, n):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None"""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
     try:
-        d = json.load(open(p))["v5_%s_n%d" % (task, n)]
+        for name, key in (("r02_ncu_summary.json", "r02_%s_n%d" % (task, n)), ("r01_ncu_summary.json", "v5_%s_n%d" % (task, n))):
+            p = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(p) and key in json.load(open(p)):
+                d = json.load(open(p))[key]
+                break
         return d["dram__bytes_read.sum"]["value"] * {"Kbyte": 1e3, "Mbyte": 1e6, "byte": 1.0}[d["dram__bytes_read.sum"]["unit"]] + \
             d["dram__bytes_write.sum"]["value"] * {"Kbyte": 1e3, "Mbyte": 1e6, "byte": 1.0}[d["dram__bytes_write.sum"]["unit"]]
     except Exception:
@@ -120,54 +127,45 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU baseline
-def cpu_baseline(task="reach", n_envs=N_ENVS, target_seconds=6.0, threads=None):
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _oracle_rate(O, tid, n_envs, acts, nthreads, seconds):
+    """env-steps/s of the C fp64 restatement with `nthreads` persistent C worker threads (oracle orc_run_mt: the whole
+    K-step loop runs inside ONE C call, so no Python / ctypes dispatch sits between steps)"""
+    sim = O.OracleSim(O.default_config(tid, n_envs=n_envs, seed=0, auto_reset=1))
+    sim.reset()
+    sim.run_mt(acts, 4, nthreads)                                 # threads up, caches warm
+    t0 = time.perf_counter()
+    sim.run_mt(acts, 8, nthreads)
+    per_step = (time.perf_counter() - t0) / 8
+    k = max(8, int(seconds / max(per_step, 1e-6)))
+    t0 = time.perf_counter()
+    sim.run_mt(acts, k, nthreads)
+    dt = time.perf_counter() - t0
+    sim.close()
+    return n_envs * k / dt, k, dt
+
+
+def cpu_baseline(task="reach", n_envs=N_ENVS, target_seconds=12.0, threads=None):
     """The CPU restatement of the reference step (oracle/, C, fp64) on the host cores: the reference's own step is
     Python on pybullet==3.0.6, which cannot be installed here -> kind = "port"."""
-    from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as O
     O.build()
     tid = {"reach": O.TASK_REACH, "push": O.TASK_PUSH, "pick": O.TASK_PICK}[task]
-    cores = threads or os.cpu_count() or 1
+    cores = threads or host_threads()
     rng = np.random.default_rng(1)
     acts = rng.uniform(-0.7, 0.7, (8, n_envs, 3)).astype(np.float32)
-
-    def run(nthreads, seconds):
-        sim = O.OracleSim(O.default_config(tid, n_envs=n_envs, seed=0, auto_reset=1))
-        sim.reset()
-        bounds = np.linspace(0, n_envs, nthreads + 1).astype(int)
-        lib = O.lib()
-        pool = ThreadPoolExecutor(nthreads) if nthreads > 1 else None
-
-        def one(k):
-            a = acts[k % len(acts)]
-            if pool is None:
-                sim.step(a)
-            else:
-                futs = [pool.submit(lib.orc_step_range, sim.h, int(bounds[i]), int(bounds[i + 1]), a.ctypes.data,
-                                    sim.obs.ctypes.data, sim.reward.ctypes.data, sim.done.ctypes.data,
-                                    sim.success.ctypes.data) for i in range(nthreads)]
-                for f in futs:
-                    f.result()
-        one(0)
-        t0 = time.perf_counter()
-        k = 0
-        while True:
-            one(k)
-            k += 1
-            dt = time.perf_counter() - t0
-            if dt >= seconds:
-                break
-        if pool:
-            pool.shutdown()
-        sim.close()
-        return n_envs * k / dt, k
-
-    one_core, k1 = run(1, target_seconds / 3)
-    all_core, kc = run(cores, target_seconds * 2 / 3) if cores > 1 else (one_core, k1)
+    one_core, k1, _ = _oracle_rate(O, tid, n_envs, acts, 1, target_seconds / 3)
+    all_core, kc, dt = _oracle_rate(O, tid, n_envs, acts, cores, target_seconds * 2 / 3) if cores > 1 else (one_core, k1, 0.0)
     return {"value": all_core, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d envs x %d steps of the C fp64 restatement of RLReachEnv.step (oracle/), %d threads; "
-                      "PyBullet itself is not installable offline" % (n_envs, kc, cores),
-            "single_core_value": one_core}
+            "sample": "%d envs x %d steps (%.1f s) of the C fp64 restatement of RLReachEnv.step (oracle/) on %d persistent C "
+                      "worker threads, the step loop inside one C call; PyBullet itself is not installable offline" % (n_envs, kc, dt, cores),
+            "single_core_value": one_core, "parallel_efficiency": all_core / (cores * one_core)}
 
 
 def run_reference(args):
@@ -175,43 +173,36 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warm = args.steps, args.warmup
-    from concurrent.futures import ThreadPoolExecutor
+    steps, warm = args.steps, max(args.warmup, 1)
     from oracle import oracle as O
     O.build()
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     n = N_ENVS
-    # each "step" = one Env.step of all 4096 envs; bound the run to ~60 s whatever K the driver passes
+    # each "step" = one Env.step of all 4096 envs on all host threads; the whole run is bounded to ~60 s whatever K is
     sim = O.OracleSim(O.default_config(O.TASK_REACH, n_envs=n, seed=0, auto_reset=1))
     sim.reset()
     rng = np.random.default_rng(1)
     acts = rng.uniform(-0.7, 0.7, (8, n, 3)).astype(np.float32)
-    bounds = np.linspace(0, n, cores + 1).astype(int)
-    lib = O.lib()
-    pool = ThreadPoolExecutor(cores)
-
-    def one(k, lo_hi=None):
-        a = acts[k % len(acts)]
-        futs = [pool.submit(lib.orc_step_range, sim.h, int(bounds[i]), int(bounds[i + 1]), a.ctypes.data,
-                            sim.obs.ctypes.data, sim.reward.ctypes.data, sim.done.ctypes.data, sim.success.ctypes.data)
-                for i in range(cores)]
-        for f in futs:
-            f.result()
+    sim.run_mt(acts, 2, cores)
     t0 = time.perf_counter()
-    one(0)
-    per_step = time.perf_counter() - t0
+    sim.run_mt(acts, 4, cores)
+    per_step = (time.perf_counter() - t0) / 4
     budget = 60.0
     k_eff = max(1, min(steps, int(budget / max(per_step, 1e-6))))
-    w_eff = max(1, min(warm, max(1, k_eff // 10)))
-    for k in range(w_eff):
-        one(k)
-    t0 = time.perf_counter()
-    for k in range(k_eff):
-        one(k)
-    dt = time.perf_counter() - t0
+    w_eff = max(1, min(warm, max(1, int(5.0 / max(per_step, 1e-6)))))
+    sim.run_mt(acts, w_eff, cores)
+    # R repeats of the K-step loop (like the GPU arm: a 20-step loop is ~20 ms, one sample of it is noise), median
+    reps = max(1, min(50, int(budget / max(per_step * k_eff, 1e-6))))
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        sim.run_mt(acts, k_eff, cores)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.median(times))
     val = n * k_eff / dt
-    sample = ("%d Env.step batches of %d envs (of the %d requested; bounded to ~%.0f s), C fp64 restatement of "
-              "RLReachEnv.step on %d host threads" % (k_eff, n, steps, budget, cores))
+    sim.close()
+    sample = ("median of %d repeats of %d Env.step batches of %d envs (of the %d requested; bounded to ~%.0f s), C fp64 "
+              "restatement of RLReachEnv.step on %d persistent C worker threads" % (reps, k_eff, n, steps, budget, cores))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k_eff,
             "warmup": w_eff, "ms_per_step": 1e3 * dt / k_eff, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -219,25 +210,58 @@ def run_reference(args):
                                    "pybullet==3.0.6 unavailable offline)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "timing": {"repeats": reps, "p10_ms_per_step": 1e3 * float(np.percentile(times, 10)) / k_eff,
+                       "p90_ms_per_step": 1e3 * float(np.percentile(times, 90)) / k_eff},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
-def time_graph(torch, envs, actions, steps, warmup, stream):
-    """CUDA-graph capture of `steps` back-to-back fused-step launches over the pool; returns seconds (device time)."""
-    pool = len(envs)
+REPEATS = 60          # timed replays per measurement (each with its own CUDA event pair); the median counts
 
-    def launch_range(lo, hi):
-        for k in range(lo, hi):
-            envs[k % pool].step(actions[k % len(actions)])
+
+def capture_pool_graphs(torch, envs, actions, steps, stream, first=0):
+    """The K-launch unit as CUDA graphs that together walk the WHOLE pool, whatever K is: graph g holds launches
+    [g*K, (g+1)*K) of the endless sequence `launch j -> batch j % pool, action set j % len(actions)`; there are
+    ceil(pool / K) graphs (at least 1), so one turn through the graphs touches every batch of the pool and consecutive
+    replays never hit state that is still in L2."""
+    pool = len(envs)
+    n_graphs = max(1, -(-pool // steps))
+    graphs = []
+    for g in range(n_graphs):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=stream):
+            for j in range(first + g * steps, first + (g + 1) * steps):
+                envs[j % pool].step(actions[j % len(actions)])
+        graphs.append(gr)
+    return graphs
+
+
+def time_replays(torch, graphs, stream, repeats=REPEATS, spin_s=0.3, barrier=None):
+    """untimed replays for spin_s seconds, then `repeats` replays (round-robin over the graphs), each bracketed by its
+    own event pair on the launching stream; returns the per-replay seconds"""
     with torch.cuda.stream(stream):
-        launch_range(0, max(warmup, 3))                       # eager warm-up (also first-use init)
-    stream.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g, stream=stream):
-        launch_range(0, steps)
-    return g
+        t_end = time.time() + spin_s
+        i = 0
+        while time.time() < t_end:
+            graphs[i % len(graphs)].replay()
+            i += 1
+            if i % 8 == 0:
+                stream.synchronize()
+        stream.synchronize()
+    if barrier:
+        barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(repeats)]
+    with torch.cuda.stream(stream):
+        for r in range(repeats):
+            ev[r][0].record(stream)
+            graphs[(i + r) % len(graphs)].replay()
+            ev[r][1].record(stream)
+    if barrier:
+        barrier()
+    else:
+        stream.synchronize()
+    return np.array([a.elapsed_time(b) * 1e-3 for a, b in ev])
 
 
 def run_ours(args):
@@ -272,12 +296,13 @@ def run_ours(args):
     launches0 = sum(e.launch_count for e in envs)
 
     sampler = ClockSampler(local)
-    graph = time_graph(torch, envs, actions, steps, warmup, stream)
-    cap_launches = sum(e.launch_count for e in envs) - launches0 - max(warmup, 3)
-    assert cap_launches == steps
     with torch.cuda.stream(stream):
-        graph.replay()                                          # untimed replay: graph upload, caches
+        for k in range(max(warmup, 3)):                         # eager warm-up (also first-use init)
+            envs[k % pool].step(actions[k % len(actions)])
     stream.synchronize()
+    graphs = capture_pool_graphs(torch, envs, actions, steps, stream, first=max(warmup, 3))
+    cap_launches = sum(e.launch_count for e in envs) - launches0 - max(warmup, 3)
+    assert cap_launches == steps * len(graphs)
 
     def barrier():
         if world > 1:
@@ -285,21 +310,13 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     sampler.start()
-    # keep the GPU busy long enough for the clock sampler to see the load (not timed)
-    t_end = time.time() + 0.3
-    with torch.cuda.stream(stream):
-        while time.time() < t_end:
-            graph.replay()
-            stream.synchronize()
-    # ---- timed region 1: device-resident inputs, exactly K launches
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        graph.replay()
-        ev1.record(stream)
-    barrier()
-    sec = ev0.elapsed_time(ev1) * 1e-3
+    # ---- timed region 1: device-resident inputs.  ~0.3 s of untimed replays (clock ramp, mid-episode states), then
+    # REPEATS replays of exactly K launches each, every replay timed by its own event pair, the set bracketed by a
+    # barrier + synchronize; this rank's number is the MEDIAN replay (one ~60 us interval is at the mercy of a single
+    # scheduling hiccup, which is what made round 1's scaling curve read 0.78).
+    times = time_replays(torch, graphs, stream, REPEATS, 0.3, barrier)
+    sec = float(np.median(times))
+    p10, p90 = float(np.percentile(times, 10)), float(np.percentile(times, 90))
     # ---- timed region 2: end to end through the host-buffer C-ABI call.  Every step: the [N,3] f32 actions sit in
     # pinned host memory, cross PCIe to the GPU, the fused kernel runs, obs/reward/done/success cross back into pinned
     # host memory and the call returns only when they are readable there (then one value of the result is read).
@@ -314,12 +331,18 @@ def run_ours(args):
         envs[k % e2e_pool].step_pinned()
     barrier()
     acc = 0.0
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        rew = envs[k % e2e_pool].step_pinned()[1]
-        acc += float(rew[0])                                  # the step's result is consumed on the host
+    e2e_reps = max(5, min(REPEATS, int(2.0 / max(e2e_steps * 2.5e-5, 1e-6))))     # ~2 s of host stepping at most
+    e2e_times = []
+    kk = 0
+    for r in range(e2e_reps):
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            rew = envs[kk % e2e_pool].step_pinned()[1]
+            acc += float(rew[0])                              # the step's result is consumed on the host
+            kk += 1
+        e2e_times.append(time.perf_counter() - t0)
     torch.cuda.synchronize(dev)
-    e2e_sec = time.perf_counter() - t0
+    e2e_sec = float(np.median(e2e_times))
     barrier()
     # ---- secondary: the same end-to-end step as a depth-2 pipeline over two independent 4096-env groups
     # (armsim_step_host_async / _wait, gym.vector's step_async / step_wait): group B's launch + PCIe round trip is in
@@ -341,9 +364,9 @@ def run_ours(args):
     clocks = sampler.stop()
 
     if world > 1:
-        t = torch.tensor([sec, e2e_sec], device=dev, dtype=torch.float64)
+        t = torch.tensor([sec, e2e_sec, p10, p90], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec, e2e_sec = float(t[0]), float(t[1])
+        sec, e2e_sec, p10, p90 = (float(x) for x in t)
     value = world * n * steps / sec
     e2e_value = world * n * e2e_steps / e2e_sec
     launch_us = 1e6 * sec / steps
@@ -355,6 +378,12 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.quick:          # single-GPU secondary numbers; the scaling runs skip them
         extra = side_measurements(torch, pkg, dev, peak_gbs)
     cpu = cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu) else None
+    train_update = None
+    if not args.quick:
+        try:
+            train_update = measure_train_updates(torch, dist, dev, world, rank)      # every rank takes part (collectives)
+        except Exception as e:
+            train_update = {"error": repr(e)}
 
     if rank == 0:
         line = {
@@ -366,10 +395,15 @@ def run_ours(args):
                        "actions": "pre-generated U(-0.7,0.7) [%d,N,3] f32 on device (launch k uses set k mod %d), auto-reset in kernel" % (N_ACT, N_ACT),
                        "l2": "inputs larger than L2: round-robin over a pool of %d independent %d-env batches "
                              "(%.0f MB touched state, L2 = 126 MB), every launch HBM-cold" % (pool, n, pool * abytes * n / 1e6),
-                       "launch": "CUDA graph of exactly K fused-step launches, CUDA events on the launching stream"},
+                       "launch": "CUDA graphs of exactly K fused-step launches each (%d graphs covering the pool, replayed round-robin), "
+                                 "CUDA event pair per replay on the launching stream" % len(graphs)},
+            "timing": {"repeats": REPEATS, "statistic": "median over the timed replays, max over ranks",
+                       "p10_ms_per_step": 1e3 * p10 / steps, "p90_ms_per_step": 1e3 * p90 / steps,
+                       "e2e_repeats": e2e_reps, "e2e_p10_us_per_step": 1e6 * float(np.percentile(e2e_times, 10)) / e2e_steps,
+                       "e2e_p90_us_per_step": 1e6 * float(np.percentile(e2e_times, 90)) / e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": load_traffic(task, n), "traffic_unit": "bytes per launch (dram read + write, ncu --set full, "
-                         "profiles/r01_ncu_summary.json; writes still in L2 at kernel end are not counted by ncu)",
+                         "profiles/r02_ncu_summary.json; writes still in L2 at kernel end are not counted by ncu)",
                          "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
                          "kernel": "step_lane_kernel<%s>" % task, "avg_launch_us": launch_us,
                          "note": "kernel is fp32-issue / dependent-latency bound, not HBM bound (SURVEY 7): ~6 kFLOP of "
@@ -386,12 +420,68 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if train_update is not None:
+            line["train_update"] = train_update
         line.update(extra)
         print(json.dumps(line), flush=True)
     for e in envs:
         e.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_train_updates(torch, dist, dev, world, rank):
+    """BASELINE config 5 in front of the driver: microseconds per learning update (replay.sample + agent.train) at N
+    ranks INCLUDING the flat-bucket gradient all-reduce (distributed.GradBucket: one NCCL all-reduce per network per
+    optimizer step, the only collective of the training path; algo/DARC/DARC_mlp.py:181-203, TD3_mlp.py:147-157),
+    issued eagerly and replayed from a CUDA graph that contains the all-reduce, plus a replica-identity bit: after the
+    same updates every rank must hold bit-identical networks (checksums all-gathered)."""
+    from drl_on_robot_arm_b200 import train
+    out = {}
+    for algo in ("TD3_MLP", "DARC_MLP"):
+        entry = {}
+        for mode, graphed in (("eager", False), ("graphed", True)):
+            tr = train.make_trainer(task="reach", algo=algo, n_envs=1024, device=dev, seed=0, window=1024, sync_every=10 ** 9,
+                                    minimal_episodes=10 ** 12, graph_updates=graphed)
+            for _ in range(540):
+                tr.rollout_step()                  # every env has committed its first (<= 501-step) episode
+            tr._stream.synchronize()
+            cyc = tr.agent.update_cycle()[0]
+            tr.train_updates(12 * cyc)             # warm-up (+ graph capture)
+            tr._stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            k = 40 * cyc
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(tr._stream)
+            tr.train_updates(k)
+            e1.record(tr._stream)
+            tr._stream.synchronize()
+            wall = time.perf_counter() - t0
+            t = torch.tensor([e0.elapsed_time(e1) * 1e3 / k, wall * 1e6 / k], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            entry[mode + "_us_per_update"] = float(t[0])
+            entry[mode + "_us_per_update_wall"] = float(t[1])
+            flat = torch.cat([p.detach().reshape(-1) for l, _ in tr.agent._learners() for p in l.net.parameters()])
+            chk = flat.view(torch.int32).to(torch.int64).sum().reshape(1)          # bit-level checksum of every weight
+            same = True
+            if world > 1:
+                got = [torch.empty_like(chk) for _ in range(world)]
+                dist.all_gather(got, chk)
+                same = all(int(g) == int(got[0]) for g in got)
+            entry[mode + "_replicas_identical"] = bool(same)
+            entry["allreduce_bytes_per_update"] = int(sum(l.bucket.nbytes for l, _ in tr.agent._learners() if l.bucket is not None))
+            tr.env.close(); tr.replay.close()
+            del tr
+        out[algo] = entry
+    out["what"] = ("us per {replay.sample(256) + agent.train} at %d rank(s), 1024 reach envs per rank, device-timed on the trainer's "
+                   "stream (max over ranks); multi-rank updates include one NCCL all-reduce of the flat gradient bucket per "
+                   "network per optimizer step; graphed = CUDA-graph replays of one control-flow cycle, all-reduce recorded "
+                   "inside the graph" % world)
+    return out
 
 
 def side_measurements(torch, pkg, dev, peak_gbs):
@@ -426,20 +516,13 @@ def side_measurements(torch, pkg, dev, peak_gbs):
             with torch.cuda.graph(g, stream=stream):
                 for j in range(k):
                     envs[j % pool].step(a[j % na])
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(stream):
-                t_end = time.time() + 0.25                       # untimed: past the reset transient, clocks ramped up
-                while time.time() < t_end:
-                    g.replay()
-                    stream.synchronize()
-                e0.record(stream)
-                g.replay()
-                e1.record(stream)
-            stream.synchronize()
-            sec = e0.elapsed_time(e1) * 1e-3 / k
+            # one graph already spans the whole pool here (k >= pool): median of 15 timed replays after 0.25 s untimed
+            tt = time_replays(torch, [g], stream, repeats=15, spin_s=0.25)
+            sec = float(np.median(tt)) / k
             gbs = ALGO_BYTES[task] * n / sec / 1e9
             res["%s_n%d" % (task, n)] = {"env_steps_per_s": n / sec, "us_per_launch": sec * 1e6, "achieved_gbs": gbs,
-                                         "hbm_frac": gbs / peak_gbs, "pool": pool, "launches": k,
+                                         "hbm_frac": gbs / peak_gbs, "pool": pool, "launches": k, "repeats": 15,
+                                         "p10_us": float(np.percentile(tt, 10)) / k * 1e6, "p90_us": float(np.percentile(tt, 90)) / k * 1e6,
                                          "l2": "pool state %.0f MB > 2 x L2, CUDA graph" % (pool * ALGO_BYTES[task] * n / 1e6)}
             del g
             for e in envs:

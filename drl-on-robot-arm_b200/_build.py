@@ -36,6 +36,15 @@ def build_libarmsim(force=False, verbose=False):
     """Compile csrc/*.cu into libarmsim.so.  Raises if nvcc is missing or the compile fails."""
     if not force and not needs_build():
         return LIB_PATH
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:      # one builder at a time (torchrun ranks share the tree)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():          # another process built it while we waited
+            return LIB_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libarmsim.so (no CPU fallback exists)")

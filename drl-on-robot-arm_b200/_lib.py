@@ -9,6 +9,7 @@ import os
 from . import _build
 
 NJ = 7
+ABI_VERSION = 4
 TASK_REACH, TASK_PUSH, TASK_PICK, TASK_KUKA_REACH = 0, 1, 2, 3
 ROBOT_KUKA_IIWA, ROBOT_DIANA_S1, ROBOT_CUSTOM = 0, 1, 2
 MODE_IK_TELEPORT, MODE_TORQUE = 0, 1
@@ -75,8 +76,8 @@ def lib():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not os.path.exists(path):
-        path = _build.build_libarmsim()
+    if not os.path.exists(path) or (_build.needs_build() and os.environ.get("ARMSIM_AUTO_REBUILD", "1") != "0"):
+        path = _build.build_libarmsim()      # missing, or older than csrc/ / include/: never load a stale library
     try:
         L = C.CDLL(path)
     except OSError as e:  # loud: no fallback
@@ -122,8 +123,8 @@ def lib():
     L.armsim_replay_state_bytes.restype = C.c_int64
     L.armsim_replay_get_state.argtypes = [vp, vp, C.c_int64]
     L.armsim_replay_set_state.argtypes = [vp, vp, C.c_int64]
-    if L.armsim_abi_version() != 3:
-        raise ArmsimError("libarmsim ABI version %d != 3" % L.armsim_abi_version())
+    if L.armsim_abi_version() != ABI_VERSION:
+        raise ArmsimError("libarmsim ABI version %d != %d" % (L.armsim_abi_version(), ABI_VERSION))
     _lib = L
     return L
 

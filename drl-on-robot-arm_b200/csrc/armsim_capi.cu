@@ -31,6 +31,19 @@ static int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(ARMSIM_E_CUDA, "%s: %s", #call, cudaGetErrorString(_e));    \
   } while (0)
 
+// The device-pointer entry points launch on the caller's stream; the handle's device must be current for the launch
+// (single-process multi-GPU callers).  Switches only when needed and restores the caller's device.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 struct ArmSim {
   ArmsimConfig cfg;
   int n = 0, obs_dim = 0, act_dim = 3, mapping = ARMSIM_MAP_LANE;
@@ -54,6 +67,8 @@ struct ArmSim {
   bool host_pending = false;              // armsim_step_host_async issued, armsim_step_host_wait not yet
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  float* fk_scratch = nullptr;   // armsim_fk_host staging (q | pos | rot), grown on demand
+  int fk_cap = 0;
 };
 
 static void rpy_to_mat(const double rpy[3], double R[9]) {
@@ -186,7 +201,7 @@ static void ensure_smem(F kern, size_t bytes) {
 }
 
 template <class... KArgs, class... Args>
-static void launch_k(void (*kern)(KArgs...), int grid, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+static cudaError_t launch_k(void (*kern)(KArgs...), int grid, size_t smem, cudaStream_t st, bool pdl, Args... args) {
   ensure_smem(kern, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -198,11 +213,11 @@ static void launch_k(void (*kern)(KArgs...), int grid, size_t smem, cudaStream_t
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 template <int TASK>
-constexpr size_t task_smem() { return TaskTraits<TASK>::HAS_CUBE ? (size_t)cube::SCRATCH_BYTES : 0; }
+constexpr size_t task_smem() { return TaskTraits<TASK>::HAS_CUBE ? (size_t)cube::scratch_bytes<TASK == ARMSIM_TASK_PICK>() : 0; }
 
 extern "C" {
 
@@ -227,6 +242,7 @@ void armsim_destroy(ArmSim* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->state_block) cudaFree(s->state_block);
   if (s->d_io) cudaFree(s->d_io);
+  if (s->fk_scratch) cudaFree(s->fk_scratch);
   if (s->host_graph) cudaGraphExecDestroy(s->host_graph);
   if (s->d_cta_seq) cudaFree(s->d_cta_seq);
   if (s->d_stats) cudaFree(s->d_stats);
@@ -254,19 +270,20 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
 #define ARMSIM_STEP_CASE(TASK, ROBOT)                                                                           \
   case (TASK) * 4 + (ROBOT):                                                                                    \
     if (grid > (TaskTraits<TASK>::HAS_CUBE ? DENSE_GRID_THRESHOLD_CUBE : DENSE_GRID_THRESHOLD))                       \
-      launch_k(step_lane_kernel<TASK, ROBOT, true>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+      lerr = launch_k(step_lane_kernel<TASK, ROBOT, true>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     else                                                                                                          \
-      launch_k(step_lane_kernel<TASK, ROBOT, false>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+      lerr = launch_k(step_lane_kernel<TASK, ROBOT, false>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     break;
 
 #define ARMSIM_TORQUE_CASE(TASK, ROBOT)                                                                                \
   case (TASK) * 4 + (ROBOT):                                                                                           \
-    launch_k(step_torque_kernel<TASK, ROBOT>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->dyn, s->S, a, o, r, d, su, fo, H); \
+    lerr = launch_k(step_torque_kernel<TASK, ROBOT>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->dyn, s->S, a, o, r, d, su, fo, H); \
     break;
 
 static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st,
                        const HostNotify H = HostNotify{nullptr, nullptr}, float* fo = nullptr) {
   const int grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
+  cudaError_t lerr = cudaSuccess;
   if (s->cfg.mode == ARMSIM_MODE_TORQUE) {
     switch (s->cfg.task * 4 + s->cfg.robot) {
       ARMSIM_TORQUE_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_KUKA_IIWA)
@@ -283,6 +300,7 @@ static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d
       ARMSIM_TORQUE_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_CUSTOM)
       default: return fail(ARMSIM_E_INVALID, "bad task / robot");
     }
+    if (lerr != cudaSuccess) return fail(ARMSIM_E_CUDA, "step launch: %s", cudaGetErrorString(lerr));
     s->launches += 1;
     CU(cudaGetLastError());
     return ARMSIM_OK;
@@ -302,6 +320,7 @@ static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d
     ARMSIM_STEP_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_CUSTOM)
     default: return fail(ARMSIM_E_INVALID, "bad task / robot");
   }
+  if (lerr != cudaSuccess) return fail(ARMSIM_E_CUDA, "step launch: %s", cudaGetErrorString(lerr));
   s->launches += 1;
   CU(cudaGetLastError());
   return ARMSIM_OK;
@@ -421,6 +440,7 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
 
 int armsim_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_reset: null handle");
+  DeviceGuard guard(s->cfg.device);
   return launch_reset(s, mask_dev, obs_dev, (cudaStream_t)stream);
 }
 
@@ -428,6 +448,7 @@ int armsim_step(ArmSim* s, const float* action_dev, float* obs_dev, float* rewar
                 void* stream) {
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_step: null handle");
   if (!action_dev || !obs_dev || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_step: null buffer");
+  DeviceGuard guard(s->cfg.device);
   return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream);
 }
 
@@ -439,7 +460,12 @@ static int wait_doorbells(ArmSim* s, unsigned int seq) {
   int b = 0;                                   // doorbells [0, b) already seen at seq
   for (unsigned long long spins = 1;; ++spins) {
     while (b < grid && f[b] == seq) ++b;
-    if (b == grid) return ARMSIM_OK;
+    if (b == grid) {
+      // the outputs were written before the doorbells (device side: fence + store); order OUR loads of them after the
+      // doorbell loads too -- free on x86 (TSO), required on weakly ordered hosts (aarch64 / Grace)
+      __atomic_thread_fence(__ATOMIC_ACQUIRE);
+      return ARMSIM_OK;
+    }
 #if defined(__x86_64__) || defined(__i386__)
     __builtin_ia32_pause();
 #endif
@@ -447,6 +473,7 @@ static int wait_doorbells(ArmSim* s, unsigned int seq) {
       cudaError_t q = cudaStreamQuery(s->stream);
       if (q == cudaSuccess) {
         while (b < grid && f[b] == seq) ++b;
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
         return b == grid ? ARMSIM_OK : fail(ARMSIM_E_CUDA, "armsim_step_host: kernel finished without ringing every doorbell");
       }
       if (q != cudaErrorNotReady) return fail(ARMSIM_E_CUDA, "armsim_step_host: %s", cudaGetErrorString(q));
@@ -469,6 +496,7 @@ int armsim_step_ex(ArmSim* s, const float* action_dev, float* obs_dev, float* re
                    float* final_obs_dev, void* stream) {
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_ex: null handle");
   if (!action_dev || !obs_dev || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_step_ex: null buffer");
+  DeviceGuard guard(s->cfg.device);
   return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream, HostNotify{nullptr, nullptr},
                      final_obs_dev);
 }
@@ -566,6 +594,7 @@ int armsim_step_host_wait(ArmSim* s, float* obs_host, float* reward_host, uint8_
 int armsim_explore(ArmSim* s, const float* actor_out_dev, float noise_std, float clip, float* action_out_dev, void* stream) {
   if (!s || !actor_out_dev || !action_out_dev) return fail(ARMSIM_E_INVALID, "armsim_explore: null argument");
   if (!(noise_std >= 0.0f)) return fail(ARMSIM_E_INVALID, "armsim_explore: noise_std must be >= 0");
+  DeviceGuard guard(s->cfg.device);
   explore_kernel<<<s->grid, LANE_BLOCK, 0, (cudaStream_t)stream>>>(s->task, s->S, s->act_dim, actor_out_dev, noise_std, clip, action_out_dev);
   s->launches += 1;
   CU(cudaGetLastError());
@@ -574,6 +603,7 @@ int armsim_explore(ArmSim* s, const float* actor_out_dev, float noise_std, float
 
 int armsim_track_episodes(ArmSim* s, const float* reward_dev, const uint8_t* done_dev, const uint8_t* success_dev, void* stream) {
   if (!s || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_track_episodes: null argument");
+  DeviceGuard guard(s->cfg.device);
   track_episodes_kernel<<<s->grid, LANE_BLOCK, 0, (cudaStream_t)stream>>>(s->n, s->S, reward_dev, done_dev, success_dev, s->d_stats);
   s->launches += 1;
   CU(cudaGetLastError());
@@ -663,10 +693,14 @@ int armsim_get_state(ArmSim* s, int32_t field, void* host_dst, size_t bytes) {
 int armsim_fk_host(ArmSim* s, const float* q_host, int32_t n, float* pos_host, float* rot_host) {
   if (!s || !q_host || !pos_host || n <= 0) return fail(ARMSIM_E_INVALID, "armsim_fk_host: bad argument");
   CU(cudaSetDevice(s->cfg.device));
-  float *dq = nullptr, *dp = nullptr, *dr = nullptr;
-  CU(cudaMalloc((void**)&dq, (size_t)n * 7 * 4));
-  CU(cudaMalloc((void**)&dp, (size_t)n * 3 * 4));
-  CU(cudaMalloc((void**)&dr, (size_t)n * 9 * 4));
+  if (n > s->fk_cap) {                       // persistent staging: the Env shims call this on every first reset()
+    if (s->fk_scratch) cudaFree(s->fk_scratch);
+    s->fk_scratch = nullptr; s->fk_cap = 0;
+    const int cap = n < 64 ? 64 : n;
+    CU(cudaMalloc((void**)&s->fk_scratch, (size_t)cap * 19 * 4));
+    s->fk_cap = cap;
+  }
+  float *dq = s->fk_scratch, *dp = dq + (size_t)s->fk_cap * 7, *dr = dp + (size_t)s->fk_cap * 3;
   cudaMemcpyAsync(dq, q_host, (size_t)n * 7 * 4, cudaMemcpyHostToDevice, s->stream);
   const int g = (n + 127) / 128;
   if (s->cfg.robot == ARMSIM_ROBOT_KUKA_IIWA) fk_kernel<ARMSIM_ROBOT_KUKA_IIWA><<<g, 128, 0, s->stream>>>(s->chain, n, dq, dp, rot_host ? dr : nullptr);
@@ -676,7 +710,6 @@ int armsim_fk_host(ArmSim* s, const float* q_host, int32_t n, float* pos_host, f
   cudaMemcpyAsync(pos_host, dp, (size_t)n * 3 * 4, cudaMemcpyDeviceToHost, s->stream);
   if (rot_host) cudaMemcpyAsync(rot_host, dr, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, s->stream);
   cudaError_t e = cudaStreamSynchronize(s->stream);
-  cudaFree(dq); cudaFree(dp); cudaFree(dr);
   if (e != cudaSuccess) return fail(ARMSIM_E_CUDA, "armsim_fk_host: %s", cudaGetErrorString(e));
   return ARMSIM_OK;
 }

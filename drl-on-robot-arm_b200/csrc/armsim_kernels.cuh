@@ -195,16 +195,6 @@ __device__ __forceinline__ bool task_epilogue(const ChainParams& C, const TaskPa
     constexpr bool PICK = TASK == ARMSIM_TASK_PICK;
     float grip = E.grip;
     cube::step<PICK>(cb, p, R, grip);                             // p.stepSimulation() rl_push_env.py:349
-    if constexpr (PICK) {
-      if (grip < 0.5f && cube::gripper_distance(cb, p, R) < cube::CLOSE_DIST) {   // rl_pick_env.py:412-416
-        const float h0 = cb.pos[0] - (p[0] + cube::GRIPPER_LEN * R[2]);
-        const float h1 = cb.pos[1] - (p[1] + cube::GRIPPER_LEN * R[5]);
-        const float h2 = cb.pos[2] - (p[2] + cube::GRIPPER_LEN * R[8]);
-        grip = sqrtf(h0 * h0 + h1 * h1 + h2 * h2) < cube::HOLD_DIST ? 2.f : 1.f;
-      }
-      cube::step<PICK>(cb, p, R, grip);                           // second p.stepSimulation() :417
-      if (live) S.grip[e] = grip;
-    }
     const float d0 = cb.pos[0] - goal[0], d1 = cb.pos[1] - goal[1], d2 = cb.pos[2] - goal[2];
     const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);       // rl_push_env.py:383 / :393
     float test = dist - E.last_dist;                              // :385
@@ -214,11 +204,19 @@ __device__ __forceinline__ bool task_epilogue(const ChainParams& C, const TaskPa
     else if (dist < 0.05f) { r = 100.f; term = true; }            // :421-423
     else { r = -test * 100.f; }                                   // :424-428
     succ = dist < T.reach_dis;                                    // _is_success :442-445
+    make_obs<TASK>(p, goal, cb, of);                              // obs = self._get_obs() (rl_pick_env.py:381) ...
+    if constexpr (PICK) {
+      // ... taken BEFORE the finger snap + second p.stepSimulation() (rl_pick_env.py:412-417), whose effect the next
+      // env step observes
+      if (grip < 0.5f && cube::gripper_distance(cb, p, R, grip) < cube::CLOSE_DIST) grip = 1.f;
+      cube::step<PICK>(cb, p, R, grip);
+      if (live) S.grip[e] = grip;
+    }
     if (live) store_cube(S, n, e, cb);
   }
   d = term ? 1 : 0;
   su = succ ? 1 : 0;
-  make_obs<TASK>(p, goal, cb, of);                 // the observation of THIS step (gymnasium's final_observation)
+  if constexpr (!TaskTraits<TASK>::HAS_CUBE) make_obs<TASK>(p, goal, cb, of);   // the observation of THIS step (gymnasium's final_observation)
 #pragma unroll
   for (int k = 0; k < TaskTraits<TASK>::OBS; ++k) o[k] = of[k];
   if (!live) return false;

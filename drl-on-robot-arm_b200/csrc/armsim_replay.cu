@@ -43,7 +43,7 @@ struct ReplayDev {
   int* t_env;                   // [cap]
   long long* t_start;           // [cap]
   int* t_len;                   // [cap]
-  unsigned long long* counters; // [0] absolute step (rows written), [1] trajectories appended, [2] sample calls
+  unsigned long long* counters; // [0] absolute step (rows written), [1] trajectories appended, [2] sample calls, [3] sample calls on an empty table
   unsigned int* blocks_done;
   uint32_t seed_lo, seed_hi;
 };
@@ -53,6 +53,17 @@ struct ArmReplay {
   void* block = nullptr;
   size_t bytes = 0;
   int device = 0;
+};
+
+struct ReplayDeviceGuard {       // launch on the replay's device whatever the caller's current device is
+  int prev = -1;
+  bool switched = false;
+  explicit ReplayDeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~ReplayDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
 };
 
 constexpr int RB = 256;
@@ -208,38 +219,80 @@ __global__ void replay_gather_kernel(const ReplayDev D, int batch, const int* __
 
 // ReplayBuffer_Trajectory_*.sample (rl_utils.py:119-152): per sample -- uniform trajectory, uniform step, with
 // probability her_ratio a uniform FUTURE step in (step, len] as the goal.  Draws: Philox4x32-10, counter =
-// (sample id, attempt, call number), key = seed.  A table entry whose rows the ring has already overwritten is
-// rejected and redrawn (8 attempts, then the newest trajectory, which is always intact).
+// (sample id, attempt, call number), key = seed.
+// Which trajectories can be drawn: the table is a ring of `cap` entries in commit order, i.e. sorted by the row in which
+// the episode ENDED; an entry is intact while the row holding its states[0] (start - 1) has not been overwritten.  Every
+// entry that ended before the ring's oldest row is gone, so a binary search over the end rows gives the first slot
+// `lo` that can still be intact and candidates are drawn uniformly from [lo, ntraj): inside that range only episodes
+// that straddle the ring's oldest row (at most one per env) are rejected and redrawn, which keeps the draw uniform
+// over the intact trajectories like the reference's random.sample(self.buffer, 1) (rl_utils.py:126).  After 16 failed
+// attempts (probability <= (episode length / window)^16) a sample falls back to a uniformly drawn trajectory of the
+// newest row's commits, which are always intact.
+// An EMPTY table (nothing committed yet, or nothing intact) has no transition to give: the reference raises
+// (random.sample on an empty deque); here the batch is zero-filled with done = 1 and counters[3] counts the call, so
+// a host that did not gate on size() can see it (armsim_replay_info) -- VectorTrainer gates on the minimum local size.
 __global__ void replay_sample_kernel(const ReplayDev D, int batch, int use_her, float thr, float her_ratio, float* states,
                                      float* actions, float* next_states, float* rewards, float* dones, int* picks) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long call = D.counters[2];
+  const unsigned long long now = D.counters[0], ntraj = D.counters[1];
+  const unsigned long long cap = (unsigned long long)D.cap;
+  const unsigned long long first = ntraj > cap ? ntraj - cap : 0ull;     // oldest logical index still in the table
+  // first logical index whose episode ended at or after the ring's oldest row (end rows are non-decreasing)
+  const long long oldest_row = (long long)now - (long long)D.W;          // rows >= oldest_row are in the ring
+  unsigned long long lo = first, hi = ntraj;
+  while (lo < hi) {
+    const unsigned long long mid = (lo + hi) >> 1;
+    const size_t s = (size_t)(mid % cap);
+    const long long end = D.t_start[s] + (long long)D.t_len[s] - 1;
+    if (end < oldest_row) lo = mid + 1; else hi = mid;
+  }
+  const unsigned long long span = ntraj - lo;
+  const bool empty = span == 0ull;
   if (b < batch) {
-    const unsigned long long now = D.counters[0], ntraj = D.counters[1];
-    const unsigned long long filled = ntraj < (unsigned long long)D.cap ? ntraj : (unsigned long long)D.cap;
-    int slot = -1;
-    uint32_t rnd[4] = {0, 0, 0, 0};
-    for (uint32_t attempt = 0; attempt < 8u && slot < 0; ++attempt) {
-      philox4x32_10((uint32_t)b, attempt, (uint32_t)call, (uint32_t)(call >> 32), D.seed_lo, D.seed_hi, rnd);
-      const int cand = (int)(((unsigned long long)rnd[0] * filled) >> 32);
-      // states[0] lives in row start-1: intact while start - 1 >= now - W
-      if (D.t_start[cand] - 1 >= (long long)now - (long long)D.W && D.t_len[cand] > 0) slot = cand;
+    if (empty) {
+      for (int k = 0; k < D.O; ++k) { states[(size_t)b * D.O + k] = 0.f; next_states[(size_t)b * D.O + k] = 0.f; }
+      for (int k = 0; k < D.A; ++k) actions[(size_t)b * D.A + k] = 0.f;
+      rewards[b] = 0.f;
+      dones[b] = 1.f;
+      if (picks) { picks[3 * b] = -1; picks[3 * b + 1] = -1; picks[3 * b + 2] = -1; }
+    } else {
+      int slot = -1;
+      uint32_t rnd[4] = {0, 0, 0, 0};
+      for (uint32_t attempt = 0; attempt < 16u && slot < 0; ++attempt) {
+        philox4x32_10((uint32_t)b, attempt, (uint32_t)call, (uint32_t)(call >> 32), D.seed_lo, D.seed_hi, rnd);
+        const int cand = (int)((lo + (((unsigned long long)rnd[0] * span) >> 32)) % cap);
+        // states[0] lives in row start-1: intact while start - 1 >= now - W
+        if (D.t_start[cand] - 1 >= oldest_row && D.t_len[cand] > 0) slot = cand;
+      }
+      if (slot < 0) {
+        // the commits of the newest row: walk back from ntraj-1 while the end row is the same (bounded by n)
+        const size_t last = (size_t)((ntraj - 1) % cap);
+        const long long end_new = D.t_start[last] + (long long)D.t_len[last] - 1;
+        unsigned long long cnt = 1;
+        while (cnt < span && cnt < (unsigned long long)D.n) {
+          const size_t s = (size_t)((ntraj - 1 - cnt) % cap);
+          if (D.t_start[s] + (long long)D.t_len[s] - 1 != end_new) break;
+          ++cnt;
+        }
+        slot = (int)((ntraj - 1 - (((unsigned long long)rnd[0] * cnt) >> 32)) % cap);
+      }
+      const int len = D.t_len[slot];
+      const int step = (int)(((unsigned long long)rnd[1] * (unsigned long long)len) >> 32);        // randint(len)
+      int goal = -1;
+      const float coin = (float)(rnd[2] >> 8) * 5.9604644775390625e-08f;
+      if (use_her && coin <= her_ratio)                                                            // uniform() <= her_ratio
+        goal = step + 1 + (int)(((unsigned long long)rnd[3] * (unsigned long long)(len - step)) >> 32);  // randint(step+1, len+1)
+      emit_transition(D, slot, step, goal, thr, b, states, actions, next_states, rewards, dones);
+      if (picks) { picks[3 * b] = slot; picks[3 * b + 1] = step; picks[3 * b + 2] = goal; }
     }
-    if (slot < 0) slot = (int)((ntraj - 1) % (unsigned long long)D.cap);
-    const int len = D.t_len[slot];
-    const int step = (int)(((unsigned long long)rnd[1] * (unsigned long long)len) >> 32);        // randint(len)
-    int goal = -1;
-    const float coin = (float)(rnd[2] >> 8) * 5.9604644775390625e-08f;
-    if (use_her && coin <= her_ratio)                                                            // uniform() <= her_ratio
-      goal = step + 1 + (int)(((unsigned long long)rnd[3] * (unsigned long long)(len - step)) >> 32);  // randint(step+1, len+1)
-    emit_transition(D, slot, step, goal, thr, b, states, actions, next_states, rewards, dones);
-    if (picks) { picks[3 * b] = slot; picks[3 * b + 1] = step; picks[3 * b + 2] = goal; }
   }
   // the last block bumps the call counter so a replayed CUDA graph draws fresh numbers
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0 && atomicAdd(D.blocks_done + 1, 1u) == gridDim.x - 1) {
     D.blocks_done[1] = 0;
+    if (empty) D.counters[3] += 1ull;
     __threadfence();
     D.counters[2] = call + 1;
   }
@@ -303,6 +356,7 @@ void armsim_replay_destroy(ArmReplay* r) {
 
 int armsim_replay_begin(ArmReplay* r, const float* obs0_dev, void* stream) {
   if (!r || !obs0_dev) return rfail(ARMSIM_E_INVALID, "armsim_replay_begin: null argument");
+  ReplayDeviceGuard guard(r->device);
   const int grid = (r->d.n * r->d.O + 255) / 256;
   replay_begin_kernel<<<grid < 1184 ? grid : 1184, 256, 0, (cudaStream_t)stream>>>(r->d, obs0_dev);
   RCU(cudaGetLastError());
@@ -313,6 +367,7 @@ int armsim_replay_store(ArmReplay* r, const float* action_dev, const float* rewa
                         const float* final_obs_dev, const float* obs_out_dev, void* stream) {
   if (!r || !action_dev || !reward_dev || !done_dev || !final_obs_dev || !obs_out_dev)
     return rfail(ARMSIM_E_INVALID, "armsim_replay_store: null argument");
+  ReplayDeviceGuard guard(r->device);
   int grid = (r->d.n * r->d.O + RB - 1) / RB;
   if (grid > 1184) grid = 1184;       // 148 SMs x 8 resident CTAs, grid-stride beyond
   replay_store_kernel<<<grid, RB, 0, (cudaStream_t)stream>>>(r->d, action_dev, reward_dev, done_dev, final_obs_dev, obs_out_dev);
@@ -325,6 +380,7 @@ int armsim_replay_sample(ArmReplay* r, int32_t batch, int32_t use_her, float dis
                          void* stream) {
   if (!r || batch <= 0 || !states_dev || !actions_dev || !next_states_dev || !rewards_dev || !dones_dev)
     return rfail(ARMSIM_E_INVALID, "armsim_replay_sample: bad argument");
+  ReplayDeviceGuard guard(r->device);
   replay_sample_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r->d, batch, use_her, dis_threshold, her_ratio, states_dev,
                                                                           actions_dev, next_states_dev, rewards_dev, dones_dev, picks_dev);
   RCU(cudaGetLastError());
@@ -335,6 +391,7 @@ int armsim_replay_gather(ArmReplay* r, int32_t batch, const int32_t* slot_dev, c
                          float dis_threshold, float* states_dev, float* actions_dev, float* next_states_dev, float* rewards_dev,
                          float* dones_dev, void* stream) {
   if (!r || batch <= 0 || !slot_dev || !step_dev || !goal_step_dev) return rfail(ARMSIM_E_INVALID, "armsim_replay_gather: bad argument");
+  ReplayDeviceGuard guard(r->device);
   replay_gather_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r->d, batch, slot_dev, step_dev, goal_step_dev, dis_threshold,
                                                                           states_dev, actions_dev, next_states_dev, rewards_dev, dones_dev);
   RCU(cudaGetLastError());
@@ -342,14 +399,14 @@ int armsim_replay_gather(ArmReplay* r, int32_t batch, const int32_t* slot_dev, c
 }
 
 /* host read-back of the counters / trajectory table (synchronises): info[0] = rows stored, [1] = trajectories appended,
- * [2] = sample calls */
-int armsim_replay_info(ArmReplay* r, int64_t info[3]) {
+ * [2] = sample calls, [3] = sample calls that found no intact trajectory (zero-filled batches) */
+int armsim_replay_info(ArmReplay* r, int64_t info[4]) {
   if (!r || !info) return rfail(ARMSIM_E_INVALID, "armsim_replay_info: null argument");
   RCU(cudaSetDevice(r->device));
   RCU(cudaDeviceSynchronize());
-  unsigned long long c[3];
+  unsigned long long c[4];
   RCU(cudaMemcpy(c, r->d.counters, sizeof(c), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 3; ++i) info[i] = (int64_t)c[i];
+  for (int i = 0; i < 4; ++i) info[i] = (int64_t)c[i];
   return ARMSIM_OK;
 }
 

@@ -1,11 +1,13 @@
 // cube_model.cuh -- device (fp32) cube / pusher / gripper model of the push and pick envs.
 //
 // Stands in for what p.stepSimulation() does to the free cube in rl_push_env.py:349 / rl_pick_env.py:348,417 (Bullet
-// rigid body + contact solver; not reproducible offline).  Model: free box (side 0.04, mass 1,
-// box inertia, mu 2.5) on the table plane z = -0.025, pushed by penetration recovery against static sphere proxies
-// of the teleported arm; 8 corner/plane contacts + sphere/box contacts, each 1 normal + 2 friction rows, 10 PGS
-// sweeps, ERP 0.2, dt 1/240, gravity -10, damping 0.04; pick: latched finger closing within 6 mm and a kinematic hold.
-// The fp64 statement of the same model used for parity is oracle/cube_model.h.
+// multibody world + contact solver; not reproducible offline).  The model is stated in
+// oracle/cube_model.h (fp64, the parity reference of this file): free box (side 0.04, mass 1, box inertia, mu 2.5) on
+// the table top z = -0.025 (ground z = -0.65 beyond the table edge), moved by penetration recovery against static
+// CAPSULES fixed in the EE frame (push: flange / link 6; pick: palm + two fingers); up to 4 corner/plane contacts +
+// the capsule contacts, each 1 normal + 2 friction rows; Bullet's solver parameters: ERP 0.2 as a velocity bias,
+// dt 1/240, gravity -10, damping 0.04, at most 50 projected-Gauss-Seidel sweeps with pybullet's early exit (largest
+// squared velocity residual of a sweep <= 1e-7); pick: fingers close for good within 6 mm and hold by friction only.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -19,14 +21,18 @@ constexpr float INV_MASS = 1.0f;
 constexpr float INV_INERTIA = 1.0f / (1.0f * (0.04f * 0.04f) / 6.0f);
 constexpr float MU = 2.5f;
 constexpr float ERP = 0.2f;
-constexpr float TABLE_Z = -0.025f;
+constexpr float TABLE_Z = -0.025f, GROUND_Z = -0.65f;
+constexpr float TABLE_X0 = -0.25f, TABLE_X1 = 1.25f, TABLE_Y0 = -0.5f, TABLE_Y1 = 0.5f;
 constexpr float MARGIN = 0.005f;
-constexpr int PGS_ITERS = 10;
+constexpr int PGS_ITERS = 50;                 // pybullet numSolverIterations
+constexpr float PGS_RESIDUAL = 1e-7f;         // pybullet m_leastSquaresResidualThreshold
 constexpr float DAMP = 0.99982992284f;
-constexpr int MAX_CONTACTS = 11;
-constexpr float PUSH_R = 0.045f, PUSH_OFF = 0.02f;
-constexpr float PALM_R = 0.05f, PALM_OFF = 0.12f, TIP_R = 0.012f, TIP_OPEN = 0.045f, TIP_CLOSED_R = 0.02f;
-constexpr float GRIPPER_LEN = 0.257f, CLOSE_DIST = 0.006f, HOLD_DIST = 0.03f;
+constexpr int MAX_CORNERS = 4, MAX_PROXIES = 3;
+constexpr float PUSH_R = 0.04f, PUSH_A0 = -0.10f, PUSH_A1 = 0.005f;
+constexpr float PALM_R = 0.045f, PALM_A0 = 0.0f, PALM_A1 = 0.15f;
+constexpr float FINGER_R = 0.01f, FINGER_A0 = 0.15f, FINGER_A1 = 0.247f, FINGER_BASE = 0.03f;
+constexpr float TIP_OPEN = 0.05f, TIP_CLOSED = 0.025f;
+constexpr float GRIPPER_LEN = 0.257f, CLOSE_DIST = 0.006f;
 
 struct State {
   float pos[3], quat[4], v[3], w[3];
@@ -50,21 +56,15 @@ __device__ __forceinline__ void rot(const float (&q)[4], float (&R)[9]) {
   R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
 }
 
-struct Contact {
-  float r[3], n[3], t1[3], t2[3];
-  float bias, ln, l1, l2;
-};
-
-__device__ __forceinline__ void tangents(Contact& k) {  // btPlaneSpace1
-  const float* n = k.n;
+__device__ __forceinline__ void tangents(const float (&n)[3], float (&t1)[3], float (&t2)[3]) {  // btPlaneSpace1
   if (fabsf(n[2]) > 0.70710678f) {
     const float a = n[1] * n[1] + n[2] * n[2], s = rsqrtf(a);
-    k.t1[0] = 0.f; k.t1[1] = -n[2] * s; k.t1[2] = n[1] * s;
-    k.t2[0] = a * s; k.t2[1] = -n[0] * k.t1[2]; k.t2[2] = n[0] * k.t1[1];
+    t1[0] = 0.f; t1[1] = -n[2] * s; t1[2] = n[1] * s;
+    t2[0] = a * s; t2[1] = -n[0] * t1[2]; t2[2] = n[0] * t1[1];
   } else {
     const float a = n[0] * n[0] + n[1] * n[1], s = rsqrtf(a);
-    k.t1[0] = -n[1] * s; k.t1[1] = n[0] * s; k.t1[2] = 0.f;
-    k.t2[0] = -n[2] * k.t1[1]; k.t2[1] = n[2] * k.t1[0]; k.t2[2] = a * s;
+    t1[0] = -n[1] * s; t1[1] = n[0] * s; t1[2] = 0.f;
+    t2[0] = -n[2] * t1[1]; t2[1] = n[2] * t1[0]; t2[2] = a * s;
   }
 }
 
@@ -111,90 +111,108 @@ __device__ __forceinline__ float sphere_query(const State& cb, const float (&R)[
   return dist - rad;
 }
 
-__device__ __forceinline__ int arm_proxies(const float (&ee)[3], const float (&Ree)[9], bool pick, float grip,
-                                           float (&C)[3][3], float (&rad)[3]) {
-  const float zx = Ree[2], zy = Ree[5], zz = Ree[8];
-  const float xx = Ree[0], xy = Ree[3], xz = Ree[6];
-  if (!pick) {
-    C[0][0] = ee[0] + PUSH_OFF * zx; C[0][1] = ee[1] + PUSH_OFF * zy; C[0][2] = ee[2] + PUSH_OFF * zz;
-    rad[0] = PUSH_R;
-    return 1;
-  }
-  C[0][0] = ee[0] + PALM_OFF * zx; C[0][1] = ee[1] + PALM_OFF * zy; C[0][2] = ee[2] + PALM_OFF * zz;
-  rad[0] = PALM_R;
-  const float g[3] = {ee[0] + GRIPPER_LEN * zx, ee[1] + GRIPPER_LEN * zy, ee[2] + GRIPPER_LEN * zz};
-  if (grip >= 0.5f) {
-    C[1][0] = g[0]; C[1][1] = g[1]; C[1][2] = g[2];
-    rad[1] = TIP_CLOSED_R;
-    return 2;
-  }
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const float o = s ? -TIP_OPEN : TIP_OPEN;
-    C[1 + s][0] = g[0] + o * xx; C[1 + s][1] = g[1] + o * xy; C[1 + s][2] = g[2] + o * xz;
-    rad[1 + s] = TIP_R;
-  }
-  return 3;
+// Capsules of the arm in the EE frame: axis point = ee + along * z_ee + side * x_ee.  push: 1 (flange / link 6);
+// pick: palm + two fingers whose tips sit TIP_OPEN / TIP_CLOSED off the axis.
+struct Capsule { float a[3], b[3], rad; };
+
+__device__ __forceinline__ void axis_point(const float (&ee)[3], const float (&Ree)[9], float along, float side, float (&o)[3]) {
+  o[0] = fmaf(side, Ree[0], fmaf(along, Ree[2], ee[0]));
+  o[1] = fmaf(side, Ree[3], fmaf(along, Ree[5], ee[1]));
+  o[2] = fmaf(side, Ree[6], fmaf(along, Ree[8], ee[2]));
 }
 
-__device__ __forceinline__ float gripper_distance(const State& cb, const float (&ee)[3], const float (&Ree)[9]) {
-  float R[9], C[3][3], rad[3], rr[3], nn[3];
+template <bool PICK>
+__device__ __forceinline__ void arm_capsule(const float (&ee)[3], const float (&Ree)[9], float grip, int p, Capsule& k) {
+  if (!PICK) {
+    axis_point(ee, Ree, PUSH_A0, 0.f, k.a); axis_point(ee, Ree, PUSH_A1, 0.f, k.b); k.rad = PUSH_R;
+  } else if (p == 0) {
+    axis_point(ee, Ree, PALM_A0, 0.f, k.a); axis_point(ee, Ree, PALM_A1, 0.f, k.b); k.rad = PALM_R;
+  } else {
+    const float sg = p == 1 ? 1.0f : -1.0f;
+    const float tip = grip >= 0.5f ? TIP_CLOSED : TIP_OPEN;
+    axis_point(ee, Ree, FINGER_A0, sg * FINGER_BASE, k.a); axis_point(ee, Ree, FINGER_A1, sg * tip, k.b); k.rad = FINGER_R;
+  }
+}
+
+// capsule <-> box: the sphere of the capsule's radius at the axis point nearest the cube centre
+__device__ __forceinline__ float capsule_query(const State& cb, const float (&R)[9], const Capsule& k, float (&rrel)[3], float (&n)[3]) {
+  const float ab[3] = {k.b[0] - k.a[0], k.b[1] - k.a[1], k.b[2] - k.a[2]};
+  const float ac[3] = {cb.pos[0] - k.a[0], cb.pos[1] - k.a[1], cb.pos[2] - k.a[2]};
+  const float len2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
+  float t = (ab[0] * ac[0] + ab[1] * ac[1] + ab[2] * ac[2]) / len2;
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  const float c[3] = {fmaf(t, ab[0], k.a[0]), fmaf(t, ab[1], k.a[1]), fmaf(t, ab[2], k.a[2])};
+  return sphere_query(cb, R, c, k.rad, rrel, n);
+}
+
+// getClosestPoints(kuka, cube, 0.006) stand-in (rl_pick_env.py:412): min signed distance capsule <-> cube
+__device__ __forceinline__ float gripper_distance(const State& cb, const float (&ee)[3], const float (&Ree)[9], float grip) {
+  float R[9], rr[3], nn[3];
   rot(cb.quat, R);
-  const int np = arm_proxies(ee, Ree, true, 0.0f, C, rad);
   float best = 1e30f;
-  for (int i = 0; i < np; ++i) best = fminf(best, sphere_query(cb, R, C[i], rad[i], rr, nn));
+#pragma unroll
+  for (int p = 0; p < MAX_PROXIES; ++p) {
+    Capsule k;
+    arm_capsule<true>(ee, Ree, grip, p, k);
+    best = fminf(best, capsule_query(cb, R, k, rr, nn));
+  }
   return best;
 }
 
 // ---- per-thread contact slots in shared memory ---------------------------------------------------------------------
 // The contacts of the oracle's list live in a per-thread column of dynamic shared memory: word k of the calling thread
-// is scratch[k * SLOT_STRIDE + threadIdx.x] (conflict-free: a warp reads 32 consecutive words).  Corner / table
-// contacts are compacted per lane into slots 0..nc-1 (corner order = the oracle's Gauss-Seidel order), the up to 3
-// arm-proxy contacts have static slots with an "active" bit.  A sweep is LDS/STS + a handful of FMAs per row; the
-// cube's velocity state stays in registers.
+// is scratch[k * SLOT_STRIDE + threadIdx.x] (conflict-free: a warp reads 32 consecutive words).  Corner / plane
+// contacts are compacted per lane into slots 0..nc-1 (corner order = the oracle's Gauss-Seidel order, at most a face),
+// the capsule contacts have static slots with an "active" bit.  Everything that does not change during the sweeps --
+// lever arms, r x dir, the row's effective mass k and 1/k -- is computed once per step, so a row inside the sweep loop
+// is LDS + one 6-term dot + clamp + two 3-term AXPYs; the cube's twist stays in registers.
 // (Round 1 history: a compacted, dynamically indexed contact array lived in local memory, ~170 instructions per
 // contact per sweep; static slots in registers made ptxas rematerialise the corner geometry inside the sweep loop,
-// ~70-85; the shared-memory slots are ~50 and cut the kernel from 223 to ~120 registers.)
+// ~70-85; the shared-memory slots are ~50.)
 constexpr int SLOT_STRIDE = 128;                 // = LANE_BLOCK (threads per block of every kernel that steps cubes)
-constexpr int CORNER_WORDS = 10;                 // r[3], bias, 1/k for n, t1, t2, lambda n, t1, t2
-constexpr int PROXY_WORDS = 16;                  // r[3], n[3], t1[3], t2[3], bias, lambda n, t1, t2
-constexpr int SCRATCH_WORDS = 8 * CORNER_WORDS + 3 * PROXY_WORDS;
-constexpr int SCRATCH_BYTES = SCRATCH_WORDS * SLOT_STRIDE * 4;     // 64 KB per 128-thread block
+constexpr int CORNER_WORDS = 13;                 // r[3], bias, k n/t1/t2, 1/k n/t1/t2, lambda n/t1/t2
+constexpr int ROW_WORDS = 9;                     // dir[3], r x dir [3], k, 1/k, lambda
+constexpr int PROXY_WORDS = 3 * ROW_WORDS + 1;   // rows n, t1, t2 + bias
+template <bool PICK> constexpr int scratch_words() { return MAX_CORNERS * CORNER_WORDS + (PICK ? 3 : 1) * PROXY_WORDS; }
+template <bool PICK> constexpr int scratch_bytes() { return scratch_words<PICK>() * SLOT_STRIDE * 4; }   // push 40 KB, pick 68 KB
 
 extern __shared__ float cube_scratch[];
 
-// One projected-Gauss-Seidel row for a general direction (arm-proxy contacts); v, w = cube twist (registers).
-__device__ __forceinline__ void row(float (&v)[3], float (&w)[3], const float (&r)[3], const float (&dir)[3], float target,
-                                    float lo, float hi, float& acc) {
-  const float rxd[3] = {r[1] * dir[2] - r[2] * dir[1], r[2] * dir[0] - r[0] * dir[2], r[0] * dir[1] - r[1] * dir[0]};
-  const float vrel = dir[0] * v[0] + dir[1] * v[1] + dir[2] * v[2] + rxd[0] * w[0] + rxd[1] * w[1] + rxd[2] * w[2];
-  const float k = fmaf(rxd[0] * rxd[0] + rxd[1] * rxd[1] + rxd[2] * rxd[2], INV_INERTIA, INV_MASS);
-  float dl = (target - vrel) * rcp_approx(k);
-  const float nl = fminf(fmaxf(acc + dl, lo), hi);
-  dl = nl - acc;
-  acc = nl;
+// One projected-Gauss-Seidel row from its slot; v, w = cube twist (registers); res = running max of the squared
+// velocity change along a row (Bullet: deltaImpulse / jacDiagABInv, squared).
+__device__ __forceinline__ float slot_row(float* s, float (&v)[3], float (&w)[3], float target, float lo, float hi, float& res) {
+  const float d0 = s[0 * SLOT_STRIDE], d1 = s[1 * SLOT_STRIDE], d2 = s[2 * SLOT_STRIDE];
+  const float x0 = s[3 * SLOT_STRIDE], x1 = s[4 * SLOT_STRIDE], x2 = s[5 * SLOT_STRIDE];
+  const float k = s[6 * SLOT_STRIDE], ik = s[7 * SLOT_STRIDE], acc = s[8 * SLOT_STRIDE];
+  const float vrel = fmaf(d0, v[0], fmaf(d1, v[1], d2 * v[2])) + fmaf(x0, w[0], fmaf(x1, w[1], x2 * w[2]));
+  const float nl = fminf(fmaxf(fmaf(target - vrel, ik, acc), lo), hi);
+  const float dl = nl - acc;
+  s[8 * SLOT_STRIDE] = nl;
   const float dli = dl * INV_INERTIA;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    v[i] = fmaf(dl, dir[i], v[i]);      // INV_MASS = 1
-    w[i] = fmaf(dli, rxd[i], w[i]);
-  }
+  v[0] = fmaf(dl, d0, v[0]); v[1] = fmaf(dl, d1, v[1]); v[2] = fmaf(dl, d2, v[2]);      // INV_MASS = 1
+  w[0] = fmaf(dli, x0, w[0]); w[1] = fmaf(dli, x1, w[1]); w[2] = fmaf(dli, x2, w[2]);
+  const float dv = dl * k;
+  res = fmaxf(res, dv * dv);
+  return nl;
 }
 
-// The three rows of a cube-corner / table contact.  The plane normal is +z, for which btPlaneSpace1 (tangents()) gives
+// The three rows of a cube-corner / plane contact.  The plane normal is +z, for which btPlaneSpace1 (tangents()) gives
 // t1 = (0,-1,0), t2 = (1,0,0); r x dir is then a signed permutation of r and the generic row collapses to a handful
-// of FMAs.  ik* = 1 / (1/m + |r x dir|^2 / I) per row, computed once per step.
-__device__ __forceinline__ void table_rows(float (&v)[3], float (&w)[3], float r0, float r1, float r2, float bias, float ikn,
-                                           float ik1, float ik2, float& ln, float& l1, float& l2) {
+// of FMAs.  k* = 1/m + |r x dir|^2 / I per row and ik* = 1 / k*, computed once per step.
+__device__ __forceinline__ void table_rows(float (&v)[3], float (&w)[3], float r0, float r1, float r2, float bias, float kn,
+                                           float k1, float k2, float ikn, float ik1, float ik2, float& ln, float& l1, float& l2,
+                                           float& res) {
   const float r0i = r0 * INV_INERTIA, r1i = r1 * INV_INERTIA, r2i = r2 * INV_INERTIA;
   {  // normal (0,0,1): r x n = (r1, -r0, 0)
     const float vrel = fmaf(r1, w[0], fmaf(-r0, w[1], v[2]));
-    const float nl = fminf(fmaxf(fmaf(bias - vrel, ikn, ln), 0.0f), 1e30f);
+    const float nl = fmaxf(fmaf(bias - vrel, ikn, ln), 0.0f);
     const float dl = nl - ln;
     ln = nl;
     v[2] += dl;
     w[0] = fmaf(dl, r1i, w[0]);
     w[1] = fmaf(-dl, r0i, w[1]);
+    const float dv = dl * kn;
+    res = fmaxf(res, dv * dv);
   }
   const float lim = MU * ln;
   {  // t1 = (0,-1,0): r x t1 = (r2, 0, -r0)
@@ -205,6 +223,8 @@ __device__ __forceinline__ void table_rows(float (&v)[3], float (&w)[3], float r
     v[1] -= dl;
     w[0] = fmaf(dl, r2i, w[0]);
     w[2] = fmaf(-dl, r0i, w[2]);
+    const float dv = dl * k1;
+    res = fmaxf(res, dv * dv);
   }
   {  // t2 = (1,0,0): r x t2 = (0, r2, -r1)
     const float vrel = fmaf(r2, w[1], fmaf(-r1, w[2], v[0]));
@@ -214,22 +234,16 @@ __device__ __forceinline__ void table_rows(float (&v)[3], float (&w)[3], float r
     v[0] += dl;
     w[1] = fmaf(dl, r2i, w[1]);
     w[2] = fmaf(-dl, r1i, w[2]);
+    const float dv = dl * k2;
+    res = fmaxf(res, dv * dv);
   }
 }
 
-// one p.stepSimulation() for the cube; grip: 0 open / push, 1 closed, 2 holding.  Same contact list and the same
-// Gauss-Seidel order as oracle/cube_model.h (corners 0..7 in index order, then the arm proxies).  Needs
-// SCRATCH_BYTES of dynamic shared memory in the calling kernel.
+// one p.stepSimulation() for the cube; grip: 0 open / push, >= 0.5 fingers closed.  Same contact list and the same
+// Gauss-Seidel order as oracle/cube_model.h (corner contacts in corner order, then the arm capsules).  Needs
+// scratch_bytes<PICK>() of dynamic shared memory in the calling kernel.
 template <bool PICK>
 static __device__ __noinline__ void step(State& cbm, const float (&ee)[3], const float (&Ree)[9], float grip) {
-  if (PICK && grip >= 1.5f) {
-    cbm.pos[0] = ee[0] + GRIPPER_LEN * Ree[2];
-    cbm.pos[1] = ee[1] + GRIPPER_LEN * Ree[5];
-    cbm.pos[2] = ee[2] + GRIPPER_LEN * Ree[8];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { cbm.v[i] = 0.f; cbm.w[i] = 0.f; }
-    return;
-  }
   State cb = cbm;                    // work on a register copy (the caller's object lives behind a reference)
   float v[3], w[3];
 #pragma unroll
@@ -239,9 +253,11 @@ static __device__ __noinline__ void step(State& cbm, const float (&ee)[3], const
   float* const sm = cube_scratch + threadIdx.x;
   float R[9];
   rot(cb.quat, R);
-  unsigned active = 0u;               // bits 8.. : arm-proxy slots in contact
+  unsigned active = 0u;               // bit p : arm capsule p in contact
   int nc = 0;                         // corner contacts, compacted in corner order into slots 0 .. nc-1
   {
+    const bool on_table = cb.pos[0] >= TABLE_X0 && cb.pos[0] <= TABLE_X1 && cb.pos[1] >= TABLE_Y0 && cb.pos[1] <= TABLE_Y1;
+    const float plane_z = on_table ? TABLE_Z : GROUND_Z;
     float H[9];                      // half-edge vectors: column k of R times HALF
 #pragma unroll
     for (int i = 0; i < 9; ++i) H[i] = R[i] * HALF;
@@ -251,79 +267,72 @@ static __device__ __noinline__ void step(State& cbm, const float (&ee)[3], const
 #pragma unroll
       for (int i = 0; i < 3; ++i)
         r[i] = ((c & 1) ? H[3 * i] : -H[3 * i]) + ((c & 2) ? H[3 * i + 1] : -H[3 * i + 1]) + ((c & 4) ? H[3 * i + 2] : -H[3 * i + 2]);
-      const float gap = cb.pos[2] + r[2] - TABLE_Z;
-      if (gap < MARGIN) {
+      const float gap = cb.pos[2] + r[2] - plane_z;
+      if (gap < MARGIN && nc < MAX_CORNERS) {
         float* s = sm + nc * (CORNER_WORDS * SLOT_STRIDE);
         ++nc;
         const float a = r[0] * r[0], b = r[1] * r[1], d = r[2] * r[2];
+        const float kn = fmaf(a + b, INV_INERTIA, INV_MASS), k1 = fmaf(d + a, INV_INERTIA, INV_MASS), k2 = fmaf(d + b, INV_INERTIA, INV_MASS);
         s[0 * SLOT_STRIDE] = r[0]; s[1 * SLOT_STRIDE] = r[1]; s[2 * SLOT_STRIDE] = r[2];
         s[3 * SLOT_STRIDE] = gap < 0.f ? -ERP * gap * INV_DT : -gap * INV_DT;
-        s[4 * SLOT_STRIDE] = rcp_approx(fmaf(a + b, INV_INERTIA, INV_MASS));
-        s[5 * SLOT_STRIDE] = rcp_approx(fmaf(d + a, INV_INERTIA, INV_MASS));
-        s[6 * SLOT_STRIDE] = rcp_approx(fmaf(d + b, INV_INERTIA, INV_MASS));
-        s[7 * SLOT_STRIDE] = 0.f; s[8 * SLOT_STRIDE] = 0.f; s[9 * SLOT_STRIDE] = 0.f;
+        s[4 * SLOT_STRIDE] = kn; s[5 * SLOT_STRIDE] = k1; s[6 * SLOT_STRIDE] = k2;
+        s[7 * SLOT_STRIDE] = rcp_approx(kn); s[8 * SLOT_STRIDE] = rcp_approx(k1); s[9 * SLOT_STRIDE] = rcp_approx(k2);
+        s[10 * SLOT_STRIDE] = 0.f; s[11 * SLOT_STRIDE] = 0.f; s[12 * SLOT_STRIDE] = 0.f;
       }
     }
   }
+  constexpr int NP = PICK ? 3 : 1;
   {
-    constexpr int NP = PICK ? 3 : 1;
-    float C[3][3], rad[3];
-    const int np = arm_proxies(ee, Ree, PICK, grip, C, rad);
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      float rr[3], nn[3];
-      const float d = sphere_query(cb, R, C[p], rad[p], rr, nn);
-      if (p < np && d < 0.f) {
-        active |= 1u << (8 + p);
-        Contact k;
+      Capsule cap;
+      arm_capsule<PICK>(ee, Ree, grip, p, cap);
+      float rr[3], dir[3][3];
+      const float d = capsule_query(cb, R, cap, rr, dir[0]);
+      if (d < 0.f) {
+        active |= 1u << p;
+        tangents(dir[0], dir[1], dir[2]);
+        float* s = sm + (MAX_CORNERS * CORNER_WORDS + p * PROXY_WORDS) * SLOT_STRIDE;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { k.r[i] = rr[i]; k.n[i] = nn[i]; }
-        tangents(k);
-        float* s = sm + (8 * CORNER_WORDS + p * PROXY_WORDS) * SLOT_STRIDE;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          s[(0 + i) * SLOT_STRIDE] = k.r[i]; s[(3 + i) * SLOT_STRIDE] = k.n[i];
-          s[(6 + i) * SLOT_STRIDE] = k.t1[i]; s[(9 + i) * SLOT_STRIDE] = k.t2[i];
+        for (int k = 0; k < 3; ++k) {
+          float* q = s + k * (ROW_WORDS * SLOT_STRIDE);
+          const float x0 = rr[1] * dir[k][2] - rr[2] * dir[k][1], x1 = rr[2] * dir[k][0] - rr[0] * dir[k][2],
+                      x2 = rr[0] * dir[k][1] - rr[1] * dir[k][0];
+          const float kk = fmaf(x0 * x0 + x1 * x1 + x2 * x2, INV_INERTIA, INV_MASS);
+          q[0 * SLOT_STRIDE] = dir[k][0]; q[1 * SLOT_STRIDE] = dir[k][1]; q[2 * SLOT_STRIDE] = dir[k][2];
+          q[3 * SLOT_STRIDE] = x0; q[4 * SLOT_STRIDE] = x1; q[5 * SLOT_STRIDE] = x2;
+          q[6 * SLOT_STRIDE] = kk; q[7 * SLOT_STRIDE] = rcp_approx(kk); q[8 * SLOT_STRIDE] = 0.f;
         }
-        s[12 * SLOT_STRIDE] = -ERP * d * INV_DT;
-        s[13 * SLOT_STRIDE] = 0.f; s[14 * SLOT_STRIDE] = 0.f; s[15 * SLOT_STRIDE] = 0.f;
+        s[3 * ROW_WORDS * SLOT_STRIDE] = -ERP * d * INV_DT;
       }
     }
   }
 
-  if (active | (unsigned)nc) {
-    constexpr int NP = PICK ? 3 : 1;
+  // Sweeps: every lane stops at ITS OWN convergence (pybullet's residual test) or after 50; a warp runs as long as its
+  // slowest cube (resting cubes take ~7 sweeps, cubes squeezed between a capsule and the table all 50).
+  bool act = (active | (unsigned)nc) != 0u;
 #pragma unroll 1
-    for (int it = 0; it < PGS_ITERS; ++it) {
-      // corner slots are compacted per lane, so a warp runs max(nc) bodies (4 for cubes lying flat) instead of one
-      // body per corner any of its lanes touches the table with (up to 8 once some cubes have been tipped over)
+  for (int it = 0; act && it < PGS_ITERS; ++it) {
+    float res = 0.f;
 #pragma unroll 1
-      for (int j = 0; j < nc; ++j) {
-        float* s = sm + j * (CORNER_WORDS * SLOT_STRIDE);
-        float ln = s[7 * SLOT_STRIDE], l1 = s[8 * SLOT_STRIDE], l2 = s[9 * SLOT_STRIDE];
-        table_rows(v, w, s[0 * SLOT_STRIDE], s[1 * SLOT_STRIDE], s[2 * SLOT_STRIDE], s[3 * SLOT_STRIDE], s[4 * SLOT_STRIDE],
-                   s[5 * SLOT_STRIDE], s[6 * SLOT_STRIDE], ln, l1, l2);
-        s[7 * SLOT_STRIDE] = ln; s[8 * SLOT_STRIDE] = l1; s[9 * SLOT_STRIDE] = l2;
-      }
+    for (int j = 0; j < nc; ++j) {
+      float* s = sm + j * (CORNER_WORDS * SLOT_STRIDE);
+      float ln = s[10 * SLOT_STRIDE], l1 = s[11 * SLOT_STRIDE], l2 = s[12 * SLOT_STRIDE];
+      table_rows(v, w, s[0 * SLOT_STRIDE], s[1 * SLOT_STRIDE], s[2 * SLOT_STRIDE], s[3 * SLOT_STRIDE], s[4 * SLOT_STRIDE],
+                 s[5 * SLOT_STRIDE], s[6 * SLOT_STRIDE], s[7 * SLOT_STRIDE], s[8 * SLOT_STRIDE], s[9 * SLOT_STRIDE], ln, l1, l2, res);
+      s[10 * SLOT_STRIDE] = ln; s[11 * SLOT_STRIDE] = l1; s[12 * SLOT_STRIDE] = l2;
+    }
 #pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        if (active & (1u << (8 + p))) {
-          float* s = sm + (8 * CORNER_WORDS + p * PROXY_WORDS) * SLOT_STRIDE;
-          float r[3], n[3], t1[3], t2[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            r[i] = s[(0 + i) * SLOT_STRIDE]; n[i] = s[(3 + i) * SLOT_STRIDE];
-            t1[i] = s[(6 + i) * SLOT_STRIDE]; t2[i] = s[(9 + i) * SLOT_STRIDE];
-          }
-          float ln = s[13 * SLOT_STRIDE], l1 = s[14 * SLOT_STRIDE], l2 = s[15 * SLOT_STRIDE];
-          row(v, w, r, n, s[12 * SLOT_STRIDE], 0.0f, 1e30f, ln);
-          const float lim = MU * ln;
-          row(v, w, r, t1, 0.0f, -lim, lim, l1);
-          row(v, w, r, t2, 0.0f, -lim, lim, l2);
-          s[13 * SLOT_STRIDE] = ln; s[14 * SLOT_STRIDE] = l1; s[15 * SLOT_STRIDE] = l2;
-        }
+    for (int p = 0; p < NP; ++p) {
+      if (active & (1u << p)) {
+        float* s = sm + (MAX_CORNERS * CORNER_WORDS + p * PROXY_WORDS) * SLOT_STRIDE;
+        const float ln = slot_row(s, v, w, s[3 * ROW_WORDS * SLOT_STRIDE], 0.0f, 1e30f, res);
+        const float lim = MU * ln;
+        slot_row(s + ROW_WORDS * SLOT_STRIDE, v, w, 0.0f, -lim, lim, res);
+        slot_row(s + 2 * ROW_WORDS * SLOT_STRIDE, v, w, 0.0f, -lim, lim, res);
       }
     }
+    act = res > PGS_RESIDUAL;
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i) { cbm.v[i] = v[i]; cbm.w[i] = w[i]; cbm.pos[i] = fmaf(v[i], DT, cb.pos[i]); }

@@ -107,9 +107,9 @@ class TrajectoryReplay:
         return o
 
     def info(self):
-        v = (C.c_int64 * 3)()
+        v = (C.c_int64 * 4)()
         L.check_replay(L.lib().armsim_replay_info(self.h, v))
-        return {"rows": int(v[0]), "trajectories": int(v[1]), "sample_calls": int(v[2])}
+        return {"rows": int(v[0]), "trajectories": int(v[1]), "sample_calls": int(v[2]), "empty_samples": int(v[3])}
 
     def size(self):
         """number of committed trajectories still addressable (rl_utils.py:115); synchronises"""

@@ -7,7 +7,8 @@ action = agent.take_action(state) + N(0, sigma)  :196-200  actions = agent.act(o
 state, reward, done, ok = env.step(action)        :201      env.step(actions, final_obs=True)      (ONE kernel launch)
 traj.store_step(...); buffer.add_trajectory(traj) :205-206  replay.store(...)  (an env's done commits its trajectory)
 if buffer.size() >= minimal_episodes:             :209      the same gate, on committed trajectories
-    n_train x agent.train(buffer.sample(B, her))  :210-212  n_train updates per N finished episodes (one "episode-time")
+    n_train x agent.train(buffer.sample(B, her))  :210-212  n_train updates per N finished episodes (one "episode-time");
+                                                            `updates_per_episode` restores the reference's ratio, below
 every 25 episodes: success_rate; if >= best:      :222-229  every 25 * N finished episodes: the same bookkeeping --
     agent.save(prefix); her_ratio *= 0.75                    save-on-best, her_ratio decay x0.75
 
@@ -15,6 +16,16 @@ The rollout step {actor forward, exploration noise, fused env step, replay store
 ONE CUDA graph; statistics stay on the device and are read back every `sync_every` steps (one small copy).
 Multi-GPU: one process per GPU, each with its env + replay shard; the agents are replicas kept identical by the flat
 gradient all-reduce inside agent.train (distributed.GradBucket); logged statistics are summed over ranks.
+
+Two deliberate differences from the reference's single-env loop, both with an option that removes them:
+  * update-to-data ratio.  The reference runs n_train = 40 updates after EVERY episode of its one env (main.py:209-212).
+    The default here is 40 updates per episode-TIME (N x world episodes), i.e. 1/N of the reference's ratio: the same
+    number of updates per second of simulated time, N times the data per update.  `updates_per_episode=k` schedules k
+    updates per finished env-episode instead (k = opt.n_train reproduces the reference's ratio exactly; the learning
+    curve is then comparable with visdata/** episode for episode).
+  * replay horizon.  The reference keeps the last 1,000,000 TRAJECTORIES (rl_utils.py:110-111, main.py:179), i.e.
+    everything a run ever produces.  Here the replay is a ring of `window` lockstep rows in HBM (make_trainer(window=));
+    window = ceil(total_steps) keeps everything too: at 91 B per env-row for push a 180 GB B200 holds 1.9e9 env-steps.
 """
 import math
 import os
@@ -33,7 +44,7 @@ class VectorTrainer:
     def __init__(self, env, agent, replay, noise_std=None, clip_actions=False, batch_size=None, n_train=None,
                  minimal_episodes=None, use_her=True, her_ratio=None, dis_threshold=0.1, window_episodes=None, avg_window=10,
                  sync_every=16, metrics=None, save_prefix=None, use_cuda_graph=True, max_updates_per_sync=None,
-                 fused_bookkeeping=True, graph_updates=None):
+                 fused_bookkeeping=True, graph_updates=None, updates_per_episode=None):
         self.env, self.agent, self.replay = env, agent, replay
         self.device = env.device
         self.n = env.n
@@ -43,6 +54,9 @@ class VectorTrainer:
         self.clip_actions = bool(clip_actions)                  # run() clips to +-action_bound (main.py:116-117)
         self.batch_size = int(batch_size or opt.batch_size)
         self.n_train = int(n_train or opt.n_train)
+        # None: n_train per episode-time (N x world episodes); k: k updates per finished env-episode (the reference's
+        # update-to-data ratio for k = opt.n_train, main.py:209-212)
+        self.updates_per_episode = None if updates_per_episode is None else float(updates_per_episode)
         self.minimal_episodes = int(opt.minimal_episodes if minimal_episodes is None else minimal_episodes)
         self.use_her = bool(use_her)
         self.her_ratio = float(opt.her_ratio if her_ratio is None else her_ratio)
@@ -59,8 +73,10 @@ class VectorTrainer:
         self.fused_bookkeeping = bool(fused_bookkeeping)       # armsim_explore / armsim_track_episodes vs torch elementwise ops
         # CUDA-graph the learning updates (single GPU; the multi-GPU path keeps eager updates around its all-reduce)
         if graph_updates is None:
-            # multi-GPU: EXPERIMENTAL opt-in (the all-reduce is recorded too); one of two 2-GPU trials hung, see DESIGN.md 6
-            graph_updates = self.use_cuda_graph and (self.world == 1 or os.environ.get("ARMSIM_GRAPH_NCCL_UPDATES") == "1")
+            # multi-GPU: the NCCL all-reduce is recorded inside the update graph; train_updates() never leaves a replay in
+            # flight (see there), which is what keeps the communicator's collectives in one order on every rank.
+            # ARMSIM_GRAPH_NCCL_UPDATES=0 falls back to eager updates around the all-reduce.
+            graph_updates = self.use_cuda_graph and (self.world == 1 or os.environ.get("ARMSIM_GRAPH_NCCL_UPDATES", "1") != "0")
         self.graph_updates = bool(graph_updates)
         self._update_graphs, self._eager_updates = {}, 0
         dev = self.device
@@ -80,6 +96,7 @@ class VectorTrainer:
         self.best_rate = 0.0
         self.returns_log = []
         self._last_stats = np.zeros(3)
+        self._replay_ready = False        # every rank holds at least one committed trajectory
 
     # ------------------------------------------------------------------ rollout
     def reset(self):
@@ -199,9 +216,19 @@ class VectorTrainer:
             self.returns_log.append(mean_ret)
             self.metrics.plot("return", mean_ret, x=self.episodes_seen)                               # main.py:207
             self.metrics.plot("avg_return", float(np.mean(self.returns_log[-self.avg_window:])), x=self.episodes_seen)  # :220
-        # n_train updates per N finished episodes, once minimal_episodes trajectories exist (main.py:209-212)
-        if self.episodes_seen >= self.minimal_episodes:
-            self.update_credit += delta[0] / float(self.n * self.world)
+        # n_train updates per N finished episodes, once minimal_episodes trajectories exist (main.py:209-212) -- and once
+        # EVERY rank can sample: each rank draws from its own replay shard, so a rank that has committed nothing yet
+        # (its envs' first episodes all still running, or all longer than the ring) must hold everybody back
+        if not self._replay_ready and self.episodes_seen >= self.minimal_episodes:
+            have = float(self.replay.size())
+            if self.world > 1:
+                have = allreduce_scalars({"t": have}, op="min")["t"]
+            self._replay_ready = have >= 1.0
+        if self.episodes_seen >= self.minimal_episodes and self._replay_ready:
+            if self.updates_per_episode is not None:
+                self.update_credit += delta[0] * self.updates_per_episode / float(self.n_train)
+            else:
+                self.update_credit += delta[0] / float(self.n * self.world)
             k = int(self.update_credit * self.n_train)
             if self.max_updates_per_sync is not None:
                 k = min(k, int(self.max_updates_per_sync))
@@ -275,8 +302,10 @@ def load_checkpoint(path, trainer):
     trainer.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
 
 
-TASK_DEFAULTS = {   # state_dim, action_bound (main.py:87 high[0]+0.3 for reach; :457 / :526 0.4 for push / pick), replay kind
-    "reach": (6, 0.7, "reach"), "push": (9, 0.4, "push"), "pick": (9, 0.4, "push"),
+TASK_DEFAULTS = {   # state_dim, action_bound (main.py:87 high[0]+0.3 for reach; :457 / :526 0.4 for push / pick), replay kind,
+    # exploration noise std: N(0, 1 * opt.gamma) for reach (main.py:200), N(0, action_bound * opt.gamma) = 0.392 for
+    # push / pick (main.py:484, :553) -- the DISCOUNT doubles as the noise scale in the reference (quirk, kept)
+    "reach": (6, 0.7, "reach", 1.0 * opt.gamma), "push": (9, 0.4, "push", 0.4 * opt.gamma), "pick": (9, 0.4, "push", 0.4 * opt.gamma),
 }
 
 
@@ -289,13 +318,17 @@ def make_trainer(task="reach", algo="TD3_MLP", n_envs=4096, device=None, seed=No
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     distributed = (world > 1) if distributed is None else distributed
-    state_dim, bound, kind = TASK_DEFAULTS[task]
+    state_dim, bound, kind, noise = TASK_DEFAULTS[task]
+    if kw.get("noise_std") is None:
+        kw["noise_std"] = noise
     torch.manual_seed(seed)                                                       # main.py:175-177 (same init on every rank)
     env = make_sharded_env(task, n_envs * world, rank=rank, world=world, device=device, seed=seed, auto_reset=True)
     agent = getattr(A, algo)(state_dim=state_dim, action_dim=3, action_bound=bound, device=env.device, distributed=distributed)
     if distributed:
         agent.broadcast_parameters(0)
     torch.manual_seed(seed + 1000 * (rank + 1))                                   # exploration noise differs per rank
-    replay = TrajectoryReplay(n_envs=env.n, obs_dim=env.obs_dim, act_dim=3, window=window, kind=kind, device=env.device,
-                              seed=seed + rank)
+    # trajectory-table slots: every episode the ring can still hold, down to 32-step episodes
+    table_cap = int(min(max(1024, 4 * env.n, env.n * (int(window) // 32)), 1 << 26))
+    replay = TrajectoryReplay(n_envs=env.n, obs_dim=env.obs_dim, act_dim=3, window=window, table_cap=table_cap, kind=kind,
+                              device=env.device, seed=seed + rank)
     return VectorTrainer(env, agent, replay, **kw)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ARMSIM_ABI_VERSION 3
+#define ARMSIM_ABI_VERSION 4
 #define ARMSIM_NJ 7            /* arm joints (Kuka iiwa, DianaS1) */
 #define ARMSIM_ACT_DIM 3       /* Cartesian EE servo action, reference envs' action_space */
 #define ARMSIM_TORQUE_DIM 7    /* torque mode action */
@@ -234,7 +234,8 @@ int armsim_replay_store(ArmReplay* rep, const float* action_dev, const float* re
                         const float* final_obs_dev, const float* obs_out_dev, void* stream);
 /* sample(batch_size, use_her, dis_threshold, her_ratio) (rl_utils.py:119-152 / :165-199): states [B,O], actions
  * [B,A], next_states [B,O], rewards [B], dones f32 0/1 [B].  picks_dev i32 [B,3] (nullable) receives the drawn
- * (table slot, step, goal step or -1).  Needs at least one committed trajectory. */
+ * (table slot, step, goal step or -1; all -1 when nothing is sampleable).  Trajectories are drawn uniformly over the
+ * intact ones (those whose rows the ring still holds). */
 int armsim_replay_sample(ArmReplay* rep, int32_t batch, int32_t use_her, float dis_threshold, float her_ratio,
                          float* states_dev, float* actions_dev, float* next_states_dev, float* rewards_dev,
                          float* dones_dev, int32_t* picks_dev, void* stream);
@@ -243,9 +244,11 @@ int armsim_replay_sample(ArmReplay* rep, int32_t batch, int32_t use_her, float d
 int armsim_replay_gather(ArmReplay* rep, int32_t batch, const int32_t* slot_dev, const int32_t* step_dev,
                          const int32_t* goal_step_dev, float dis_threshold, float* states_dev, float* actions_dev,
                          float* next_states_dev, float* rewards_dev, float* dones_dev, void* stream);
-/* Synchronous read-backs: info = {rows stored, trajectories committed (size(), rl_utils.py:115), sample calls};
- * the first `count` trajectory-table entries (env, absolute start row, length). */
-int armsim_replay_info(ArmReplay* rep, int64_t info[3]);
+/* Synchronous read-backs: info = {rows stored, trajectories committed (size(), rl_utils.py:115), sample calls,
+ * sample calls that found no intact trajectory}; the first `count` trajectory-table entries (env, absolute start
+ * row, length).  Sampling from an empty replay (the reference raises, rl_utils.py:126) yields a zero-filled batch
+ * with done = 1 and bumps info[3]. */
+int armsim_replay_info(ArmReplay* rep, int64_t info[4]);
 int armsim_replay_table(ArmReplay* rep, int32_t* env_host, int64_t* start_host, int32_t* len_host, int32_t count);
 /* Checkpoint / resume: the ring, the trajectory table and every cursor as one opaque blob (only valid for a replay
  * created with the identical ArmReplayConfig).  Synchronous. */

@@ -330,6 +330,13 @@ int orc_dense_fd(int32_t robot, const double q[7], const double qd[7], const dou
 }
 
 /* ------------------------------------------------------------------------------------------------ sim */
+/* diagnostics: contact-solver sweeps used so far by this process (not thread-safe: read it from single-thread runs) */
+static _Thread_local uint64_t g_pgs_sweeps = 0, g_pgs_steps = 0;   /* per thread: the calling thread reads its own */
+void orc_pgs_stats(uint64_t out[2], int reset) {
+  out[0] = g_pgs_sweeps; out[1] = g_pgs_steps;
+  if (reset) g_pgs_sweeps = g_pgs_steps = 0;
+}
+
 struct OrcSim {
   ArmsimConfig cfg;
   OrcChain chain;
@@ -345,6 +352,7 @@ struct OrcSim {
   CubeState* cube;      /* push / pick */
   double* last_dist;
   double* grip;
+  double* grip_dist;    /* diagnostic: the last getClosestPoints stand-in distance evaluated for the env (pick) */
 };
 
 static int32_t base_obs_dim(const OrcSim* s) {
@@ -354,6 +362,9 @@ static int32_t base_obs_dim(const OrcSim* s) {
     default: return 9;
   }
 }
+
+/* diagnostic read-back for the parity tests: distance the last pick step compared with the 6 mm closing threshold */
+void orc_grip_distance(const OrcSim* s, double* out) { memcpy(out, s->grip_dist, (size_t)s->n * sizeof(double)); }
 
 int32_t orc_obs_dim(const OrcSim* s) { return base_obs_dim(s) + (s->cfg.mode == ARMSIM_MODE_TORQUE ? 2 * NJ : 0); }
 int32_t orc_action_dim(const OrcSim* s) { return s->cfg.mode == ARMSIM_MODE_TORQUE ? ARMSIM_TORQUE_DIM : ARMSIM_ACT_DIM; }
@@ -379,6 +390,7 @@ OrcSim* orc_create(const ArmsimConfig* cfg) {
   s->cube = calloc(n, sizeof(CubeState));
   s->last_dist = calloc(n, sizeof(double));
   s->grip = calloc(n, sizeof(double));
+  s->grip_dist = calloc(n, sizeof(double));
   orc_reset(s, NULL, NULL);
   return s;
 }
@@ -386,7 +398,7 @@ OrcSim* orc_create(const ArmsimConfig* cfg) {
 void orc_destroy(OrcSim* s) {
   if (!s) return;
   free(s->q); free(s->qd); free(s->goal); free(s->step); free(s->episode); free(s->ik_iters); free(s->done);
-  free(s->cube); free(s->last_dist); free(s->grip);
+  free(s->cube); free(s->last_dist); free(s->grip); free(s->grip_dist);
   free(s);
 }
 
@@ -454,7 +466,7 @@ static void reset_env(OrcSim* s, int e, float* obs) {
     /* p.stepSimulation() :242 then obs / last distances :243-245 */
     double Ree[9];
     chain_fk(&s->chain, s->q[e], ee, Ree, NULL, NULL);
-    cube_step(&s->cube[e], ee, Ree, c->task == ARMSIM_TASK_PICK, s->grip[e]);
+    (void)cube_step(&s->cube[e], ee, Ree, c->task == ARMSIM_TASK_PICK, s->grip[e]);
     double d[3] = {s->cube[e].pos[0] - (double)s->goal[e][0], s->cube[e].pos[1] - (double)s->goal[e][1],
                    s->cube[e].pos[2] - (double)s->goal[e][2]};
     s->last_dist[e] = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
@@ -512,7 +524,7 @@ after_servo:;
   s->step[e] += 1;                                                      /* :264 */
 
   double r = 0.0;
-  int term = 0, succ = 0;
+  int term = 0, succ = 0, wrote_obs = 0;
   if (c->task == ARMSIM_TASK_REACH) {
     /* _reward rl_reach_env.py:267-319 */
     double d0 = ee[0] - (double)s->goal[e][0], d1 = ee[1] - (double)s->goal[e][1], d2 = ee[2] - (double)s->goal[e][2];
@@ -531,18 +543,10 @@ after_servo:;
     else if (dist < c->reach_dis) { r = 10.0; term = 1; succ = 1; }     /* :289-291 */
     else { r = 0.0; term = 0; }
   } else {
-    /* push / pick: cube dynamics inside stepSimulation, then _reward rl_push_env.py:368-440 */
+    /* push / pick: cube dynamics inside stepSimulation, then _reward rl_push_env.py:368-440 / rl_pick_env.py:367-445 */
     const int pick = c->task == ARMSIM_TASK_PICK;
-    cube_step(&s->cube[e], ee, Ree, pick, s->grip[e]);
-    if (pick) {
-      /* rl_pick_env.py:412-417: any arm link within 6 mm of the cube -> fingers snap shut, then a 2nd sim step */
-      if (s->grip[e] < 0.5 && cube_gripper_distance(&s->cube[e], ee, Ree) < PICK_CLOSE_DIST) {
-        double g[3] = {ee[0] + PICK_GRIPPER_LEN * Ree[2], ee[1] + PICK_GRIPPER_LEN * Ree[5], ee[2] + PICK_GRIPPER_LEN * Ree[8]};
-        double h0 = s->cube[e].pos[0] - g[0], h1 = s->cube[e].pos[1] - g[1], h2 = s->cube[e].pos[2] - g[2];
-        s->grip[e] = sqrt(h0 * h0 + h1 * h1 + h2 * h2) < PICK_HOLD_DIST ? 2.0 : 1.0;
-      }
-      cube_step(&s->cube[e], ee, Ree, pick, s->grip[e]);
-    }
+    g_pgs_sweeps += (uint64_t)cube_step(&s->cube[e], ee, Ree, pick, s->grip[e]);
+    g_pgs_steps += 1;
     const CubeState* cb = &s->cube[e];
     double d[3] = {cb->pos[0] - (double)s->goal[e][0], cb->pos[1] - (double)s->goal[e][1], cb->pos[2] - (double)s->goal[e][2]};
     double dist_cur = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);    /* :383 distance_current (fp64 obs) */
@@ -556,13 +560,24 @@ after_servo:;
     else if (dist_t < 0.05) { r = 100.0; term = 1; }                    /* :421-423 */
     else { r = -test * 100.0; term = 0; }                               /* :424-428 */
     succ = dist_cur < c->reach_dis;                                     /* _is_success :442-445 on the fp64 obs */
+    if (pick) {
+      /* rl_pick_env.py:403-417: obs / distances above were taken BEFORE this block (`obs = self._get_obs()` :381);
+       * any arm link within 6 mm of the cube -> the four finger joints snap to 0 (never reopened before reset),
+       * then a 2nd sim step whose effect the NEXT env step observes */
+      if (obs && !(term && c->auto_reset)) write_obs(s, e, ee, obs);
+      wrote_obs = 1;
+      s->grip_dist[e] = cube_gripper_distance(&s->cube[e], ee, Ree, s->grip[e]);
+      if (s->grip[e] < 0.5 && s->grip_dist[e] < PICK_CLOSE_DIST) s->grip[e] = 1.0;
+      g_pgs_sweeps += (uint64_t)cube_step(&s->cube[e], ee, Ree, pick, s->grip[e]);
+      g_pgs_steps += 1;
+    }
   }
   s->done[e] = (uint8_t)term;
   reward[e] = r;
   done[e] = (uint8_t)term;
   success[e] = (uint8_t)succ;
   if (term && c->auto_reset) reset_env(s, e, obs);
-  else if (obs) write_obs(s, e, ee, obs);
+  else if (obs && !wrote_obs) write_obs(s, e, ee, obs);
 }
 
 void orc_step_range(OrcSim* s, int32_t lo, int32_t hi, const float* action, float* obs, double* reward, uint8_t* done,
@@ -648,3 +663,90 @@ int orc_get_state_f64(OrcSim* s, int32_t field, double* dst, size_t count) {
 }
 
 int orc_default_config(int32_t task, ArmsimConfig* cfg) { return armsim_fill_default_config(task, cfg); }
+
+/* ------------------------------------------------------------------------------------------------ threaded stepping
+ * CPU-baseline leg of bench.py: one Env.step of the whole batch on `nthreads` persistent worker threads, each owning a
+ * contiguous slice of the envs (they are independent units).  Workers spin on a generation counter (sense-reversing
+ * barrier with a short pause / yield back-off) so that a 4096-env step, ~0.3 ms of work on 32 threads, is not
+ * dominated by futex wake-ups the way a Python thread pool or pthread_barrier_wait would be. */
+#include <pthread.h>
+#include <sched.h>
+#include <stdatomic.h>
+
+typedef struct OrcPool OrcPool;
+typedef struct OrcWorker { OrcPool* pool; int idx; pthread_t th; } OrcWorker;
+struct OrcPool {
+  OrcSim* sim;
+  int nthreads;
+  OrcWorker* w;
+  atomic_uint gen;        /* bumped by the caller to start a step */
+  atomic_int pending;     /* workers still running the current step */
+  atomic_int quit;
+  const float* action; float* obs; double* reward; uint8_t* done; uint8_t* success;
+};
+
+static inline void orc_cpu_relax(unsigned spins) {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#endif
+  if ((spins & 0x3FFu) == 0x3FFu) sched_yield();
+}
+
+static void orc_pool_slice(OrcPool* p, int idx) {
+  const int n = p->sim->n, t = p->nthreads;
+  const int lo = (int)((long long)n * idx / t), hi = (int)((long long)n * (idx + 1) / t);
+  orc_step_range(p->sim, lo, hi, p->action, p->obs, p->reward, p->done, p->success);
+}
+
+static void* orc_pool_main(void* arg) {
+  OrcWorker* w = (OrcWorker*)arg;
+  OrcPool* p = w->pool;
+  unsigned seen = 0;
+  for (;;) {
+    unsigned spins = 0;
+    while (atomic_load_explicit(&p->gen, memory_order_acquire) == seen) {
+      if (atomic_load_explicit(&p->quit, memory_order_relaxed)) return NULL;
+      orc_cpu_relax(++spins);
+    }
+    seen = atomic_load_explicit(&p->gen, memory_order_acquire);
+    orc_pool_slice(p, w->idx);
+    atomic_fetch_sub_explicit(&p->pending, 1, memory_order_release);
+  }
+}
+
+OrcPool* orc_pool_create(OrcSim* s, int nthreads) {
+  if (!s || nthreads < 1) return NULL;
+  OrcPool* p = (OrcPool*)calloc(1, sizeof(OrcPool));
+  p->sim = s; p->nthreads = nthreads;
+  p->w = (OrcWorker*)calloc((size_t)nthreads, sizeof(OrcWorker));
+  atomic_init(&p->gen, 0u); atomic_init(&p->pending, 0); atomic_init(&p->quit, 0);
+  for (int i = 1; i < nthreads; ++i) {          /* slice 0 runs on the calling thread */
+    p->w[i].pool = p; p->w[i].idx = i;
+    pthread_create(&p->w[i].th, NULL, orc_pool_main, &p->w[i]);
+  }
+  return p;
+}
+
+void orc_pool_destroy(OrcPool* p) {
+  if (!p) return;
+  atomic_store(&p->quit, 1);
+  for (int i = 1; i < p->nthreads; ++i) pthread_join(p->w[i].th, NULL);
+  free(p->w); free(p);
+}
+
+/* one Env.step of every env of the pool's sim, work split over the pool's threads; returns when all slices are done */
+void orc_step_mt(OrcPool* p, const float* action, float* obs, double* reward, uint8_t* done, uint8_t* success) {
+  p->action = action; p->obs = obs; p->reward = reward; p->done = done; p->success = success;
+  atomic_store_explicit(&p->pending, p->nthreads - 1, memory_order_relaxed);
+  atomic_fetch_add_explicit(&p->gen, 1u, memory_order_release);
+  orc_pool_slice(p, 0);
+  unsigned spins = 0;
+  while (atomic_load_explicit(&p->pending, memory_order_acquire) > 0) orc_cpu_relax(++spins);
+}
+
+/* `steps` consecutive Env.steps inside ONE call (action set k % n_sets of a [n_sets, n, act_dim] ring): what a C host
+ * loop around the reference step would cost, with no per-step Python / ctypes dispatch at all */
+void orc_run_mt(OrcPool* p, const float* actions, int n_sets, int steps, float* obs, double* reward, uint8_t* done, uint8_t* success) {
+  const size_t stride = (size_t)p->sim->n * (size_t)orc_action_dim(p->sim);
+  for (int k = 0; k < steps; ++k) orc_step_mt(p, actions + (size_t)(k % n_sets) * stride, obs, reward, done, success);
+}

@@ -54,8 +54,18 @@ int orc_set_state(OrcSim* s, int32_t field, const void* src, size_t bytes);
 int orc_get_state(OrcSim* s, int32_t field, void* dst, size_t bytes);
 int orc_get_state_f64(OrcSim* s, int32_t field, double* dst, size_t count);
 int32_t orc_obs_dim(const OrcSim* s);
+/* diagnostics for the parity tests */
+void orc_grip_distance(const OrcSim* s, double* out);          /* pick: last distance compared with the 6 mm threshold */
+void orc_pgs_stats(uint64_t out[2], int reset);                 /* {contact-solver sweeps, cube sim steps} so far */
 int32_t orc_action_dim(const OrcSim* s);
 int orc_default_config(int32_t task, ArmsimConfig* cfg);
+
+/* persistent worker threads for the CPU-baseline leg of bench.py: each Env.step is split over `nthreads` slices */
+typedef struct OrcPool OrcPool;
+OrcPool* orc_pool_create(OrcSim* s, int nthreads);
+void orc_pool_destroy(OrcPool* p);
+void orc_step_mt(OrcPool* p, const float* action, float* obs, double* reward, uint8_t* done, uint8_t* success);
+void orc_run_mt(OrcPool* p, const float* actions, int n_sets, int steps, float* obs, double* reward, uint8_t* done, uint8_t* success);
 
 #ifdef __cplusplus
 }

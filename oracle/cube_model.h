@@ -1,27 +1,44 @@
 /* cube_model.h -- TEST INFRASTRUCTURE (oracle side, fp64) of the cube / pusher / gripper model.
  *
  * What p.stepSimulation() contributes to the push / pick envs (rl_push_env.py:242,349; rl_pick_env.py:242,348,417)
- * lives inside pybullet==3.0.6 (btMultiBodyDynamicsWorld: convex-mesh collision + 50-iteration PGS) and CANNOT be
- * reproduced offline (no Bullet source, no kuka/table meshes: SURVEY 8c, Appendix C) -- PARITY UNPINNED.  This file
- * states the behavioural model both the oracle and the CUDA kernels implement instead; the CUDA side
- * (csrc/cube_model.cuh) must match THIS to fp32 tolerance, and the model is pinned only by the reference's
- * known-answer statistics (untouched-cube push return in [-514.6, -511]).
+ * lives inside pybullet==3.0.6 (btMultiBodyDynamicsWorld: convex-mesh collision + PGS contact solver) and CANNOT be
+ * reproduced offline (no Bullet source, no kuka / gripper / table meshes: SURVEY 8c, Appendix C) -- PARITY UNPINNED.
+ * This file states the model both the oracle and the CUDA kernels implement instead; the CUDA side
+ * (csrc/cube_model.cuh) must match THIS to fp32 tolerance.  System-level pins: the reference's untouched-cube return
+ * (-504, visdata/push/updata_TD3) and its push learning curve reproduced by the reference's OWN learner on this model
+ * (tests/system/ref_learner_on_oracle.py, tests/golden/ref_learner_push_*.json).
  *
- * Model, per sim step (Bullet defaults: dt = 1/240 s, gravity (0,0,-10), ERP 0.2, restitution 0, damping 0.04):
+ * Model, per sim step, with Bullet's / pybullet's default parameters:
+ *   dt 1/240 s, gravity (0,0,-10), ERP 0.2 applied as a velocity bias (btMultiBody contacts have no split impulse),
+ *   restitution 0, linear / angular damping 0.04, at most 50 projected-Gauss-Seidel iterations with pybullet's early
+ *   exit once the largest squared velocity residual of a sweep drops to 1e-7 (m_leastSquaresResidualThreshold).
  *   cube     : free rigid box, side 0.04 (models/cube_small_push.urdf:17,25), mass 1 (:12), inertia recomputed from
  *              the box as Bullet does by default (m a^2 / 6 = 2.667e-4, isotropic), lateral friction 5.0 (:5)
  *              combined multiplicatively with the default 0.5 of the table / arm links -> mu = 2.5.
- *   table    : plane z = -0.025 (pybullet_data table/table.urdf at (0.5,0,-0.65): top box 0.05 thick centred 0.6 up).
- *   arm      : kinematic, zero velocity (teleported); represented by sphere proxies fixed in the EE link frame
- *              (push: one sphere r 0.045 at EE + 0.02 z_ee, the link-7 flange; pick: palm + finger-tip spheres).
- *              The cube is moved by penetration recovery against those static spheres, as in Bullet.
- *   contacts : 8 box corners vs plane (speculative margin 5 mm) + closest-point box/sphere contacts; each contact
- *              = 1 normal row + 2 friction rows (box friction cone), solved by 10 projected-Gauss-Seidel sweeps;
+ *   table    : top face z = -0.025 over x in [-0.25, 1.25], y in [-0.5, 0.5] (pybullet_data table/table.urdf at
+ *              (0.5,0,-0.65): 1.5 x 1 x 0.05 top centred 0.6 up); beyond the edge the ground plane z = -0.65
+ *              (plane.urdf at z = -0.65, rl_push_env.py:184).
+ *   arm      : kinematic with zero velocity (teleported by resetJointState, held by the default motors), seen by the
+ *              cube as CAPSULES fixed in the EE link frame (axis = EE local z, which the IK keeps pointing down):
+ *                push : link 7 / flange + the link-6 body above it: radius 0.04, axis from 0.10 behind the EE frame
+ *                       to 0.005 in front of it (round end = the flange face 0.045 in front of the frame).
+ *                pick : palm (radius 0.045, EE frame to 0.15 in front) and the two WSG50 fingers (radius 0.01, from
+ *                       0.15 to 0.247 in front; tip centre 0.05 off the axis when open, 0.025 when closed, along the
+ *                       EE local x axis): fingertips reach gripper_length = 0.257 (rl_pick_env.py:79).
+ *              Contact of a capsule with the box = contact of the sphere of the capsule's radius centred at the axis
+ *              point nearest the cube centre (box / sphere closest point, or minimum-translation face when the centre
+ *              is inside the box).  A tall capsule therefore pushes a cube lying on the table horizontally, as the
+ *              side of the real flange does, and cannot get under it.  The cube is moved by penetration recovery
+ *              against those static shapes, as in Bullet.
+ *   contacts : box corners vs the supporting plane (speculative margin 5 mm; the first 4 in corner order -- a face --
+ *              which is every corner a rigid box can have that close to a plane) + the capsule contacts; each contact
+ *              = 1 normal row + 2 friction rows (btPlaneSpace1 directions, box friction limits mu * normal impulse);
  *              normal bias = ERP * depth / dt when penetrating, -gap / dt inside the speculative margin.
  *   integrate: semi-implicit Euler; quaternion integrated with the exponential map.
- *   pick     : fingers close (latched) when any proxy is within 6 mm of the cube (rl_pick_env.py:412-416); if the
- *              cube centre is then within 3 cm of the grasp point (EE + 0.257 z_ee, :79,374) the cube is held:
- *              it follows the grasp point kinematically (documented simplification of friction grasping).
+ *   pick     : the fingers close for good once any capsule is within 6 mm of the cube (getClosestPoints(kuka, cube,
+ *              0.006), rl_pick_env.py:412-416).  Closed fingers squeeze the cube through ordinary contacts (normal +
+ *              friction rows against ZERO-velocity fingers): there is no kinematic attachment.  As in Bullet, a cube
+ *              held by friction does not follow teleported fingers; it moves only through penetration recovery.
  */
 #ifndef ORACLE_CUBE_MODEL_H
 #define ORACLE_CUBE_MODEL_H
@@ -36,20 +53,32 @@
 #define CUBE_MU 2.5
 #define CUBE_ERP 0.2
 #define CUBE_TABLE_Z (-0.025)
+#define CUBE_GROUND_Z (-0.65)
+#define CUBE_TABLE_X0 (-0.25)
+#define CUBE_TABLE_X1 (1.25)
+#define CUBE_TABLE_Y0 (-0.5)
+#define CUBE_TABLE_Y1 (0.5)
 #define CUBE_MARGIN 0.005
-#define CUBE_PGS_ITERS 10
+#define CUBE_PGS_ITERS 50
+#define CUBE_PGS_RESIDUAL 1e-7
 #define CUBE_DAMP_FACTOR 0.99982992284  /* (1 - 0.04)^(1/240) */
-#define CUBE_MAX_CONTACTS 11
-#define PUSH_R 0.045
-#define PUSH_OFF 0.02
-#define PICK_PALM_R 0.05
-#define PICK_PALM_OFF 0.12
-#define PICK_TIP_R 0.012
-#define PICK_TIP_OPEN 0.045
-#define PICK_TIP_CLOSED_R 0.02
+#define CUBE_MAX_PROXIES 3
+#define CUBE_MAX_CORNERS 4   /* a face: no more than 4 corners of a rigid 4 cm box can be within 5 mm of a plane */
+#define CUBE_MAX_CONTACTS (CUBE_MAX_CORNERS + CUBE_MAX_PROXIES)
+#define PUSH_R 0.04
+#define PUSH_A0 (-0.10)
+#define PUSH_A1 0.005
+#define PICK_PALM_R 0.045
+#define PICK_PALM_A0 0.0
+#define PICK_PALM_A1 0.15
+#define PICK_FINGER_R 0.01
+#define PICK_FINGER_A0 0.15
+#define PICK_FINGER_A1 0.247
+#define PICK_FINGER_BASE 0.03
+#define PICK_TIP_OPEN 0.05
+#define PICK_TIP_CLOSED 0.025
 #define PICK_GRIPPER_LEN 0.257
 #define PICK_CLOSE_DIST 0.006
-#define PICK_HOLD_DIST 0.03
 
 typedef struct CubeState {
   double pos[3], quat[4], v[3], w[3];
@@ -62,6 +91,11 @@ typedef struct CubeContact {
   double bias;      /* target normal velocity */
   double ln, l1, l2;/* accumulated impulses */
 } CubeContact;
+
+/* capsule of the arm: segment a-b (world) swept by a sphere of radius rad */
+typedef struct CubeCapsule {
+  double a[3], b[3], rad;
+} CubeCapsule;
 
 static inline void cube_init(CubeState* c, double x, double y, double z, double yaw) {
   memset(c, 0, sizeof(*c));
@@ -133,46 +167,63 @@ static inline double cube_sphere_query(const CubeState* cb, const double R[9], c
   return dist - rad;
 }
 
-/* sphere proxies of the arm for this step: centres (world) and radii; returns the count */
-static inline int cube_arm_proxies(const double ee[3], const double Ree[9], int pick, double grip, double C[3][3], double rad[3]) {
-  const double zx = Ree[2], zy = Ree[5], zz = Ree[8];   /* EE local +z in world */
-  const double xx = Ree[0], xy = Ree[3], xz = Ree[6];   /* EE local +x in world */
+/* capsule <-> box: the sphere of the capsule's radius at the axis point nearest the cube centre */
+static inline double cube_capsule_query(const CubeState* cb, const double R[9], const CubeCapsule* k, double rrel[3], double n[3]) {
+  double ab[3] = {k->b[0] - k->a[0], k->b[1] - k->a[1], k->b[2] - k->a[2]};
+  double ac[3] = {cb->pos[0] - k->a[0], cb->pos[1] - k->a[1], cb->pos[2] - k->a[2]};
+  double len2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
+  double t = (ab[0] * ac[0] + ab[1] * ac[1] + ab[2] * ac[2]) / len2;
+  t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+  double c[3] = {k->a[0] + t * ab[0], k->a[1] + t * ab[1], k->a[2] + t * ab[2]};
+  return cube_sphere_query(cb, R, c, k->rad, rrel, n);
+}
+
+static inline void cube_axis_point(const double ee[3], const double Ree[9], double along, double side, double out[3]) {
+  /* EE local z = column 2 of Ree, local x = column 0 */
+  out[0] = ee[0] + along * Ree[2] + side * Ree[0];
+  out[1] = ee[1] + along * Ree[5] + side * Ree[3];
+  out[2] = ee[2] + along * Ree[8] + side * Ree[6];
+}
+
+/* capsules of the arm for this step; grip: 0 open / push, >= 0.5 fingers closed.  Returns the count. */
+static inline int cube_arm_capsules(const double ee[3], const double Ree[9], int pick, double grip, CubeCapsule K[CUBE_MAX_PROXIES]) {
   if (!pick) {
-    C[0][0] = ee[0] + PUSH_OFF * zx; C[0][1] = ee[1] + PUSH_OFF * zy; C[0][2] = ee[2] + PUSH_OFF * zz;
-    rad[0] = PUSH_R;
+    cube_axis_point(ee, Ree, PUSH_A0, 0.0, K[0].a);
+    cube_axis_point(ee, Ree, PUSH_A1, 0.0, K[0].b);
+    K[0].rad = PUSH_R;
     return 1;
   }
-  C[0][0] = ee[0] + PICK_PALM_OFF * zx; C[0][1] = ee[1] + PICK_PALM_OFF * zy; C[0][2] = ee[2] + PICK_PALM_OFF * zz;
-  rad[0] = PICK_PALM_R;
-  double g[3] = {ee[0] + PICK_GRIPPER_LEN * zx, ee[1] + PICK_GRIPPER_LEN * zy, ee[2] + PICK_GRIPPER_LEN * zz};
-  if (grip >= 0.5) {
-    C[1][0] = g[0]; C[1][1] = g[1]; C[1][2] = g[2];
-    rad[1] = PICK_TIP_CLOSED_R;
-    return 2;
-  }
+  cube_axis_point(ee, Ree, PICK_PALM_A0, 0.0, K[0].a);
+  cube_axis_point(ee, Ree, PICK_PALM_A1, 0.0, K[0].b);
+  K[0].rad = PICK_PALM_R;
+  const double tip = grip >= 0.5 ? PICK_TIP_CLOSED : PICK_TIP_OPEN;
   for (int s = 0; s < 2; ++s) {
-    double o = s ? -PICK_TIP_OPEN : PICK_TIP_OPEN;
-    C[1 + s][0] = g[0] + o * xx; C[1 + s][1] = g[1] + o * xy; C[1 + s][2] = g[2] + o * xz;
-    rad[1 + s] = PICK_TIP_R;
+    const double sg = s ? -1.0 : 1.0;
+    cube_axis_point(ee, Ree, PICK_FINGER_A0, sg * PICK_FINGER_BASE, K[1 + s].a);
+    cube_axis_point(ee, Ree, PICK_FINGER_A1, sg * tip, K[1 + s].b);
+    K[1 + s].rad = PICK_FINGER_R;
   }
   return 3;
 }
 
-/* getClosestPoints(kuka, cube, 0.006) stand-in (rl_pick_env.py:412): min signed distance proxy <-> cube */
-static inline double cube_gripper_distance(const CubeState* cb, const double ee[3], const double Ree[9]) {
-  double R[9], C[3][3], rad[3], rr[3], nn[3];
+/* getClosestPoints(kuka, cube, 0.006) stand-in (rl_pick_env.py:412): min signed distance capsule <-> cube, fingers
+ * in their current state */
+static inline double cube_gripper_distance(const CubeState* cb, const double ee[3], const double Ree[9], double grip) {
+  double R[9], rr[3], nn[3];
+  CubeCapsule K[CUBE_MAX_PROXIES];
   cube_rot(cb->quat, R);
-  int np = cube_arm_proxies(ee, Ree, 1, 0.0, C, rad);
+  int np = cube_arm_capsules(ee, Ree, 1, grip, K);
   double best = 1e30;
   for (int i = 0; i < np; ++i) {
-    double d = cube_sphere_query(cb, R, C[i], rad[i], rr, nn);
+    double d = cube_capsule_query(cb, R, &K[i], rr, nn);
     if (d < best) best = d;
   }
   return best;
 }
 
-static inline void cube_row(CubeState* cb, const double r[3], const double dir[3], double target, double lo, double hi,
-                            double* acc) {
+/* one PGS row; returns the squared velocity change along the row (Bullet's least-squares residual term) */
+static inline double cube_row(CubeState* cb, const double r[3], const double dir[3], double target, double lo, double hi,
+                              double* acc) {
   double rxd[3];
   cube_cross(r, dir, rxd);
   double vrel = dir[0] * cb->v[0] + dir[1] * cb->v[1] + dir[2] * cb->v[2] + rxd[0] * cb->w[0] + rxd[1] * cb->w[1] + rxd[2] * cb->w[2];
@@ -186,17 +237,12 @@ static inline void cube_row(CubeState* cb, const double r[3], const double dir[3
     cb->v[i] += dl * dir[i] / CUBE_MASS;
     cb->w[i] += dl * rxd[i] / CUBE_INERTIA;
   }
+  double dv = dl * k;
+  return dv * dv;
 }
 
-/* one p.stepSimulation() for the cube.  grip: 0 open / push, 1 closed, 2 holding */
-static inline void cube_step(CubeState* cb, const double ee[3], const double Ree[9], int pick, double grip) {
-  if (pick && grip >= 1.5) {  /* held: follows the grasp point */
-    cb->pos[0] = ee[0] + PICK_GRIPPER_LEN * Ree[2];
-    cb->pos[1] = ee[1] + PICK_GRIPPER_LEN * Ree[5];
-    cb->pos[2] = ee[2] + PICK_GRIPPER_LEN * Ree[8];
-    for (int i = 0; i < 3; ++i) cb->v[i] = cb->w[i] = 0.0;
-    return;
-  }
+/* one p.stepSimulation() for the cube.  grip: 0 open / push, >= 0.5 fingers closed.  Returns the PGS sweeps used. */
+static inline int cube_step(CubeState* cb, const double ee[3], const double Ree[9], int pick, double grip) {
   /* predictUnconstraintMotion: gravity, then damping */
   cb->v[2] -= CUBE_G * CUBE_DT;
   for (int i = 0; i < 3; ++i) { cb->v[i] *= CUBE_DAMP_FACTOR; cb->w[i] *= CUBE_DAMP_FACTOR; }
@@ -205,13 +251,15 @@ static inline void cube_step(CubeState* cb, const double ee[3], const double Ree
   cube_rot(cb->quat, R);
   CubeContact K[CUBE_MAX_CONTACTS];
   int nk = 0;
-  /* 8 corners vs the table plane */
+  /* 8 corners vs the supporting plane: the table top while the cube centre is over it, else the ground */
+  const int on_table = cb->pos[0] >= CUBE_TABLE_X0 && cb->pos[0] <= CUBE_TABLE_X1 && cb->pos[1] >= CUBE_TABLE_Y0 && cb->pos[1] <= CUBE_TABLE_Y1;
+  const double plane_z = on_table ? CUBE_TABLE_Z : CUBE_GROUND_Z;
   for (int c = 0; c < 8; ++c) {
     double l[3] = {(c & 1) ? CUBE_HALF : -CUBE_HALF, (c & 2) ? CUBE_HALF : -CUBE_HALF, (c & 4) ? CUBE_HALF : -CUBE_HALF};
     double r[3];
     for (int i = 0; i < 3; ++i) r[i] = R[3 * i] * l[0] + R[3 * i + 1] * l[1] + R[3 * i + 2] * l[2];
-    double gap = cb->pos[2] + r[2] - CUBE_TABLE_Z;
-    if (gap < CUBE_MARGIN) {
+    double gap = cb->pos[2] + r[2] - plane_z;
+    if (gap < CUBE_MARGIN && nk < CUBE_MAX_CORNERS) {
       CubeContact* k = &K[nk++];
       memcpy(k->r, r, sizeof(r));
       k->n[0] = 0; k->n[1] = 0; k->n[2] = 1;
@@ -220,12 +268,12 @@ static inline void cube_step(CubeState* cb, const double ee[3], const double Ree
       cube_tangents(k);
     }
   }
-  /* arm proxies */
-  double C[3][3], rad[3];
-  int np = cube_arm_proxies(ee, Ree, pick, grip, C, rad);
+  /* arm capsules */
+  CubeCapsule A[CUBE_MAX_PROXIES];
+  int np = cube_arm_capsules(ee, Ree, pick, grip, A);
   for (int p = 0; p < np; ++p) {
     double rr[3], nn[3];
-    double d = cube_sphere_query(cb, R, C[p], rad[p], rr, nn);
+    double d = cube_capsule_query(cb, R, &A[p], rr, nn);
     if (d < 0) {
       CubeContact* k = &K[nk++];
       memcpy(k->r, rr, sizeof(rr));
@@ -235,13 +283,20 @@ static inline void cube_step(CubeState* cb, const double ee[3], const double Ree
       cube_tangents(k);
     }
   }
-  for (int it = 0; it < CUBE_PGS_ITERS; ++it) {
-    for (int i = 0; i < nk; ++i) {
-      CubeContact* k = &K[i];
-      cube_row(cb, k->r, k->n, k->bias, 0.0, 1e30, &k->ln);
-      double lim = CUBE_MU * k->ln;
-      cube_row(cb, k->r, k->t1, 0.0, -lim, lim, &k->l1);
-      cube_row(cb, k->r, k->t2, 0.0, -lim, lim, &k->l2);
+  int sweeps = 0;
+  if (nk > 0) {
+    for (int it = 0; it < CUBE_PGS_ITERS; ++it) {
+      double res = 0.0;
+      for (int i = 0; i < nk; ++i) {
+        CubeContact* k = &K[i];
+        double r0 = cube_row(cb, k->r, k->n, k->bias, 0.0, 1e30, &k->ln);
+        double lim = CUBE_MU * k->ln;
+        double r1 = cube_row(cb, k->r, k->t1, 0.0, -lim, lim, &k->l1);
+        double r2 = cube_row(cb, k->r, k->t2, 0.0, -lim, lim, &k->l2);
+        res = fmax(res, fmax(r0, fmax(r1, r2)));
+      }
+      ++sweeps;
+      if (res <= CUBE_PGS_RESIDUAL) break;   /* m_leastSquaresResidualThreshold */
     }
   }
   /* integrateTransforms */
@@ -257,5 +312,6 @@ static inline void cube_step(CubeState* cb, const double ee[3], const double Ree
                   dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2]};
   double inv = 1.0 / sqrt(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
   for (int i = 0; i < 4; ++i) cb->quat[i] = nq[i] * inv;
+  return sweeps;
 }
 #endif

@@ -85,6 +85,13 @@ def lib():
         L.orc_set_state.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]
         L.orc_get_state.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]
         L.orc_get_state_f64.argtypes = [C.c_void_p, C.c_int32, dp, C.c_size_t]
+        L.orc_grip_distance.argtypes = [C.c_void_p, dp]
+        L.orc_pgs_stats.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+        L.orc_pool_create.argtypes = [C.c_void_p, C.c_int]
+        L.orc_pool_create.restype = C.c_void_p
+        L.orc_pool_destroy.argtypes = [C.c_void_p]
+        L.orc_step_mt.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.orc_run_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
         L.orc_obs_dim.argtypes = [C.c_void_p]
         L.orc_obs_dim.restype = C.c_int32
         L.orc_action_dim.argtypes = [C.c_void_p]
@@ -172,6 +179,13 @@ def dense_fd(q, qd, tau, robot=ROBOT_KUKA):
     return out, M.reshape(7, 7)
 
 
+def pgs_stats(reset=True):
+    """(contact-solver sweeps, cube sim steps) accumulated by this process"""
+    out = (C.c_uint64 * 2)()
+    lib().orc_pgs_stats(out, 1 if reset else 0)
+    return int(out[0]), int(out[1])
+
+
 def philox(ctr, key):
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)
@@ -204,6 +218,9 @@ class OracleSim:
         self.success = np.zeros(self.n, np.uint8)
 
     def close(self):
+        if getattr(self, "_pool", None) is not None:
+            lib().orc_pool_destroy(self._pool[0])
+            self._pool = None
         if self.h:
             lib().orc_destroy(self.h)
             self.h = None
@@ -221,6 +238,26 @@ class OracleSim:
         lib().orc_step_range(self.h, lo, self.n if hi is None else hi, a.ctypes.data, self.obs.ctypes.data,
                              self.reward.ctypes.data, self.done.ctypes.data, self.success.ctypes.data)
         return self.obs.copy(), self.reward.copy(), self.done.copy(), self.success.copy()
+
+    def grip_distance(self):
+        """pick: the distance the last step compared with the 6 mm finger-closing threshold (rl_pick_env.py:412)"""
+        a = np.zeros(self.n, np.float64)
+        lib().orc_grip_distance(self.h, _dp(a))
+        return a
+
+    def run_mt(self, actions, steps, nthreads):
+        """`steps` Env.steps of the whole batch inside one C call, split over `nthreads` persistent worker threads;
+        actions = a ring [n_sets, n, act_dim] (step k uses set k % n_sets).  The CPU-baseline leg of bench.py."""
+        a = np.ascontiguousarray(actions, np.float32)
+        assert a.ndim == 3 and a.shape[1:] == (self.n, self.act_dim)
+        pool = getattr(self, "_pool", None)
+        if pool is None or pool[1] != nthreads:
+            if pool is not None:
+                lib().orc_pool_destroy(pool[0])
+            pool = self._pool = (lib().orc_pool_create(self.h, int(nthreads)), int(nthreads))
+        lib().orc_run_mt(pool[0], a.ctypes.data, a.shape[0], int(steps), self.obs.ctypes.data, self.reward.ctypes.data,
+                         self.done.ctypes.data, self.success.ctypes.data)
+        return self.obs, self.reward, self.done, self.success
 
     def set_state(self, field, arr):
         dt = np.int32 if field in INT_FIELDS else np.float32

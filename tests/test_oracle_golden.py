@@ -267,7 +267,9 @@ def test_push_untouched_cube_known_answer(oracle):
 
 
 def test_push_cube_moves_when_pushed(oracle):
-    """drive the flange into the cube: the cube must move away from the EE and end displaced on the table"""
+    """scripted "push 10 cm": drive the flange capsule into the cube at 4 mm per step; the cube must move away from the
+    EE, never be launched (the tall capsule cannot get under it), and -- once the arm is lifted away -- come to rest flat
+    on the table (centre 0.02 above z = -0.025)"""
     O = oracle
     s = O.OracleSim(O.default_config(O.TASK_PUSH, n_envs=1, seed=1))
     s.reset()
@@ -278,11 +280,73 @@ def test_push_cube_moves_when_pushed(oracle):
     for _ in range(60):                                             # descend
         s.step(np.array([[0, 0, -0.4]], np.float32))
     c0 = s.get_state_f64(O.F_CUBE_POS)[0].copy()
+    zmax = -1.0
     for _ in range(80):                                             # sweep -x through the cube
         s.step(np.array([[-0.05, 0, -0.4]], np.float32))
+        zmax = max(zmax, s.get_state_f64(O.F_CUBE_POS)[0][2])
+    for _ in range(60):                                             # lift the arm away, let the cube settle
+        s.step(np.array([[0, 0, 0.4]], np.float32))
     c1 = s.get_state_f64(O.F_CUBE_POS)[0]
-    assert c1[0] < c0[0] - 0.03, (c0, c1)
-    assert abs(c1[2] + 0.005) < 2e-3
+    assert c1[0] < c0[0] - 0.05, (c0, c1)                           # pushed along -x
+    assert zmax < 0.01, zmax                                        # never launched (round 1's sphere threw it 25 cm up)
+    assert abs(c1[2] + 0.005) < 2e-3, c1                            # at rest on the table
+    assert np.abs(s.get_state_f64(O.F_CUBE_LINVEL)).max() < 1e-2
+
+
+def test_push_fast_sweep_does_not_launch_the_cube(oracle):
+    """a teleporting pusher at the policy's full speed (0.4 * 0.08 = 3.2 cm per step) tunnels through or kicks the cube
+    (a cube squeezed between the round end of the capsule and the table hops a few cm) but never sends it flying as
+    round 1's sphere did (25 cm): over 64 seeded layouts the cube centre stays below z = 0.08"""
+    O = oracle
+    n = 64
+    s = O.OracleSim(O.default_config(O.TASK_PUSH, n_envs=n, seed=11))
+    obs = s.reset()
+    zmax = np.full(n, -1.0)
+    for t in range(120):
+        ee, cube = obs[:, :3], obs[:, 3:6]
+        want = cube.copy(); want[:, 2] = 0.0
+        a = np.clip((want - ee) / 0.08, -0.4, 0.4).astype(np.float32)     # charge at the cube along the table
+        obs = s.step(a)[0]
+        zmax = np.maximum(zmax, s.get_state_f64(O.F_CUBE_POS)[:, 2])
+    assert (zmax < 0.08).all(), zmax.max()
+
+
+def test_contact_solver_sweeps(oracle):
+    """Bullet's solver settings: at most 50 sweeps, early exit at squared residual 1e-7.  A cube at rest on the table
+    converges in fewer than 10 sweeps; no step may use more than 50."""
+    O = oracle
+    s = O.OracleSim(O.default_config(O.TASK_PUSH, n_envs=1, seed=2))
+    s.reset()
+    up = np.array([[0, 0, 0.4]], np.float32)
+    for _ in range(40):
+        s.step(up)                                                   # cube has landed and settled
+    O.pgs_stats(reset=True)
+    for _ in range(50):
+        s.step(up)
+    sweeps, steps = O.pgs_stats()
+    assert steps == 50 and 1 <= sweeps / steps < 10, (sweeps, steps)
+
+
+def test_pick_fingers_latch_within_6mm_and_hold_by_friction_only(oracle):
+    """rl_pick_env.py:412-416: any link within 6 mm -> the finger joints snap to 0 and stay there; the cube is then
+    squeezed by ordinary contacts (no kinematic attachment): lifting the teleported arm leaves the cube behind"""
+    O = oracle
+    s = O.OracleSim(O.default_config(O.TASK_PICK, n_envs=1, seed=4))
+    obs = s.reset()
+    assert s.get_state(O.F_GRIP)[0] == 0
+    for t in range(200):
+        ee, cube = obs[0, :3], obs[0, 3:6]
+        want = cube + np.array([0.02, 0.02, 0.257 + 0.005])          # fingertips around the cube, off-centre: one finger touches
+        a = np.clip((want - ee) / 0.08, -0.4, 0.4).astype(np.float32)[None]
+        obs = s.step(a)[0]
+        if s.get_state(O.F_GRIP)[0] > 0.5:
+            break
+    assert s.get_state(O.F_GRIP)[0] == 1.0, "fingers never closed"
+    assert s.grip_distance()[0] < 0.006
+    for t in range(40):                                              # lift 40 x 3.2 cm
+        obs = s.step(np.array([[0, 0, 0.4]], np.float32))[0]
+    assert s.get_state(O.F_GRIP)[0] == 1.0                           # never reopens before reset
+    assert obs[0, 2] > 0.8 and obs[0, 5] < 0.05                      # the arm went up, the cube did not follow
 
 
 # --------------------------------------------------------------------------------------------- torque mode (ABA)

@@ -279,51 +279,126 @@ def test_free_running_episode(pkg, oracle, torch_cuda):
 
 
 # --------------------------------------------------------------------------------------------- push / pick
-@pytest.mark.parametrize("task,tid", [("push", 1), ("pick", 2)])
-def test_cube_tasks_teacher_forced(pkg, oracle, torch_cuda, task, tid):
+DIANA_Q0 = [0.7387, 1.3985, 1.2382, 2.0372, -1.8803, -1.359, -0.2102]   # EE (0.5, 0, 0.4), tool down (oracle IK)
+
+
+@pytest.mark.parametrize("task,tid,n,robot", [("push", 1, 4096, "kuka_iiwa"), ("pick", 2, 2048, "kuka_iiwa"),
+                                               ("push", 1, 512, "diana_s1"), ("pick", 2, 512, "diana_s1")])
+def test_cube_tasks_teacher_forced(pkg, oracle, torch_cuda, task, tid, n, robot):
+    """push / pick at the BASELINE sizes (configs 3 / 4: push 4096, pick 2048) and on the DianaS1 chain: every env step
+    starts from the oracle's state (teacher forcing), so each comparison is one fused step = IK + one (push) or two
+    (pick) cube sim steps.  Tolerances (fp32 device vs fp64 oracle):
+      EE                      5e-6 m   equal IK iteration counts, converged
+                              1e-3 m   envs that ran into Bullet's 20-iteration cap (pick: joint 7 is never teleported,
+                                       rl_pick_env.py:342, so the orientation error cannot vanish): both sides made
+                                       the same 20 DLS updates, q agrees to 2e-3 rad
+      cube position / obs     5e-5 m   (up to 50 Gauss-Seidel sweeps each side; recovery speeds up to ~3 m/s), for all
+                                       but 0.5 % of the envs -- the contact set is a discontinuous function of the pose
+                                       (a corner entering the 5 mm margin, the capsule touching), so an env that sits
+                                       on such a boundary may differ by one contact for one step
+      cube velocity           5e-3 m/s (same envs)
+      finger state            equal, except envs whose closing distance is within 2e-5 m of the 6 mm threshold"""
     L, O = pkg._lib, oracle
-    n = 1024
-    env, ora = _pair(pkg, oracle, task, n, seed=8)
+    kw = {}
+    if robot == "diana_s1":
+        kw = dict(robot="diana_s1", init_q=DIANA_Q0)
+    env = pkg.ArmSimHandle(task, n_envs=n, seed=8, **kw)
+    okw = dict(kw)
+    if robot == "diana_s1":
+        okw["robot"] = O.ROBOT_DIANA
+    ora = O.OracleSim(O.default_config(tid, n_envs=n, seed=8, **okw))
     rng = np.random.default_rng(8)
     fields = [O.F_Q, O.F_CUBE_POS, O.F_CUBE_QUAT, O.F_CUBE_LINVEL, O.F_CUBE_ANGVEL, O.F_LAST_DIST, O.F_GRIP]
     # bring half of the arms down onto their cubes so that contacts are exercised
     env.reset_host()
     ora.reset()
-    for k in range(80):
+    n_cmp = n_bad = n_cap = touched = 0
+    steps = 80 if n <= 2048 else 60
+    for k in range(steps):
         _sync_state(env, ora, L, O, fields + [O.F_GOAL])
         ee = ora.obs[:, :3]
         cube = ora.get_state(O.F_CUBE_POS)
         want = cube.copy()
-        want[:, 2] += 0.03 if task == "push" else 0.257 + 0.01
+        want[:, 2] = 0.0 if task == "push" else cube[:, 2] + 0.257 + 0.005
+        want[:, :2] += rng.normal(0, 0.02, (n, 2))
         a = np.clip((want - ee) / 0.08, -0.4, 0.4).astype(np.float32)
         a[n // 2:] = rng.uniform(-0.4, 0.4, (n - n // 2, 3)).astype(np.float32)
         a += rng.normal(0, 0.05, a.shape).astype(np.float32)
+        v0 = ora.get_state(O.F_CUBE_LINVEL)
         og, rg, dg, sg = env.step_host(a)
         oo, ro, do, so = ora.step(a)
         it_g, it_o = env.get_state(L.F_IK_ITERS), ora.get_state(O.F_IK_ITERS)
-        # pick never teleports joint 7 (rl_pick_env.py:342), so every IK call starts 90 deg off in yaw and a few
-        # envs run into Bullet's 20-iteration cap without converging: no parity claim for those
         same = (it_g == it_o) & (it_o < 20)
-        assert np.abs(og[:, :3] - oo[:, :3])[same].max() <= 5e-6
+        cap = (it_g == 20) & (it_o == 20)
+        eerr = np.abs(og[:, :3] - oo[:, :3]).max(axis=1)
+        assert eerr[same].max() <= 5e-6
+        if cap.any():
+            n_cap += int(cap.sum())
+            assert eerr[cap].max() <= 1e-3, eerr[cap].max()
+            assert np.abs(env.get_state(L.F_Q) - ora.get_state(O.F_Q))[cap].max() <= 2e-3
         gg, go = env.get_state(L.F_GRIP), ora.get_state(O.F_GRIP)
-        ok = same & (gg == go)
-        assert ok.mean() > 0.97
-        # one cube step from identical state: positions to 5e-5 m (10 PGS sweeps in fp32 vs fp64, recovery speeds up to ~2 m/s); a HELD cube sits
-        # at the grasp point 0.257 m down the tool axis, so its position inherits the EE orientation difference
-        # (<= 4e-4 rad between fp32 and fp64 IK paths) times that lever arm: 1e-4 m
-        cerr = np.abs(og[:, 3:6] - oo[:, 3:6]).max(axis=1)
-        held = go >= 1.5
-        assert cerr[ok & ~held].max() <= 5e-5, (k, cerr[ok & ~held].max())
-        if (ok & held).any():
-            assert cerr[ok & held].max() <= 1e-4, (k, cerr[ok & held].max())
-        assert np.array_equal(og[:, 6:], oo[:, 6:])
+        ok = same | cap
+        if task == "pick":
+            gd = ora.grip_distance()
+            diff = ok & (gg != go)
+            assert (np.abs(gd[diff] - 0.006) <= 2e-5).all(), gd[diff]      # only threshold straddlers may disagree
+            ok = ok & (gg == go)
+        # obs[3:6] = the cube after the (first) sim step of this env step; state = after the last one
+        cerr = np.maximum(np.abs(og[:, 3:6] - oo[:, 3:6]).max(axis=1),
+                          np.abs(env.get_state(L.F_CUBE_POS) - ora.get_state(O.F_CUBE_POS)).max(axis=1))
         verr = np.abs(env.get_state(L.F_CUBE_LINVEL) - ora.get_state(O.F_CUBE_LINVEL)).max(axis=1)
-        assert verr[ok].max() <= 5e-3, (k, verr[ok].max())
+        tol_pos = np.where(cap, 2e-4, 5e-5)          # capped IK: the capsule itself sits up to 1e-3 m elsewhere
+        bad = ok & ((cerr > tol_pos) | (verr > 5e-3))
+        n_cmp += int(ok.sum()); n_bad += int(bad.sum())
+        touched += int((np.abs(ora.get_state(O.F_CUBE_LINVEL)[:, :2]).max(axis=1) > 0.05).sum())
+        assert np.array_equal(og[:, 6:], oo[:, 6:])
         dist = np.linalg.norm(oo[:, 3:6] - oo[:, 6:], axis=1)
-        clear = ok & (np.abs(dist - 0.05) > 1e-4)
+        clear = ok & ~bad & (np.abs(dist - 0.05) > 1e-4)
         assert np.array_equal(dg[clear], do[clear]) and np.array_equal(sg[clear], so[clear])
+        moving = clear & (do == 0)
+        assert np.abs(rg - ro)[moving & (np.abs(np.abs(ro) - 1.0) > 1e-6)].max(initial=0) <= 2e-2   # r = -100 * (distance change)
+    assert n_cmp > 0.97 * n * steps and n_bad <= 0.005 * n_cmp, (n_cmp, n_bad)
+    assert touched > 0.02 * n * steps, touched            # contacts with the arm were really exercised
     if task == "pick":
         assert (ora.get_state(O.F_GRIP) > 0).any()          # some grippers did close on their cube
+    env.close()
+
+
+def test_cube_free_running_statistics(pkg, oracle, torch_cuda):
+    """push, no teacher forcing, 300 steps of a cube-chasing policy at n = 1024: contact dynamics are chaotic, so the
+    comparison is statistical -- the device and the oracle must agree on how far cubes get pushed and how often the
+    episode ends in success, and no cube may be launched on either side"""
+    L, O = pkg._lib, oracle
+    n = 1024
+    env, ora = _pair(pkg, oracle, "push", n, seed=21)
+    og, oo = env.reset_host(), ora.reset()
+    start = oo[:, 3:6].copy()
+    rng = np.random.default_rng(21)
+    zg = np.full(n, -1.0); zo = np.full(n, -1.0)
+    sg_tot = so_tot = 0
+    alive_g = np.ones(n, bool); alive_o = np.ones(n, bool)
+    for k in range(300):
+        noise = rng.normal(0, 0.2, (n, 3)).astype(np.float32)
+
+        def act(obs):
+            ee, cube, tgt = obs[:, :3], obs[:, 3:6], obs[:, 6:9]
+            d = tgt - cube; d[:, 2] = 0
+            d /= np.linalg.norm(d, axis=1, keepdims=True) + 1e-9
+            want = cube - 0.07 * d; want[:, 2] = 0.0
+            behind = np.linalg.norm((want - ee)[:, :2], axis=1) < 0.03
+            a = np.clip((want - ee) / 0.08, -0.4, 0.4)
+            a[behind] = 0.15 * d[behind]
+            return (a + noise).astype(np.float32)
+        og, rg, dg, sg = env.step_host(act(og))
+        oo, ro, do, so = ora.step(act(oo))
+        sg_tot += int((sg.astype(bool) & alive_g).sum()); so_tot += int((so.astype(bool) & alive_o).sum())
+        alive_g &= ~dg.astype(bool); alive_o &= ~do.astype(bool)
+        zg = np.maximum(zg, og[:, 5]); zo = np.maximum(zo, oo[:, 5])
+    assert zg.max() < 0.1 and zo.max() < 0.1                          # nobody launched
+    mg = np.linalg.norm(og[:, 3:5] - start[:, :2], axis=1)[alive_g]
+    mo = np.linalg.norm(oo[:, 3:5] - start[:, :2], axis=1)[alive_o]
+    assert abs(np.median(mg) - np.median(mo)) < 0.02 + 0.25 * np.median(mo), (np.median(mg), np.median(mo))
+    assert abs(sg_tot - so_tot) <= 0.05 * n + 0.3 * so_tot, (sg_tot, so_tot)
     env.close()
 
 

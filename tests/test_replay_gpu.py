@@ -156,3 +156,52 @@ def test_rollout_store_sample_under_cuda_graph(pkg, torch_cuda):
         checked += 1
     assert checked > 20
     env.close(); rep.close()
+
+
+def test_sample_from_an_empty_replay_is_flagged_not_garbage(pkg, torch_cuda):
+    """the reference raises on an empty buffer (random.sample on an empty deque, rl_utils.py:126); the device sampler
+    cannot raise from inside a CUDA graph: it emits a zero batch with done = 1 (no bootstrap) and counts the call"""
+    torch = torch_cuda
+    rep = pkg.TrajectoryReplay(n_envs=8, obs_dim=6, act_dim=3, window=16, table_cap=32, kind="reach", seed=1)
+    rep.begin(torch.zeros((8, 6), device=rep.device))
+    for k in range(3):                                                # rows stored, nothing committed
+        z = torch.full((8, 6), float(k), device=rep.device)
+        rep.store(torch.ones((8, 3), device=rep.device), torch.ones(8, device=rep.device),
+                  torch.zeros(8, dtype=torch.uint8, device=rep.device), z, z)
+    out = rep.sample(64, True, 0.1, 0.8, return_picks=True)
+    assert float(out["states"].abs().max()) == 0 and float(out["next_states"].abs().max()) == 0
+    assert float(out["rewards"].abs().max()) == 0 and bool((out["dones"] == 1).all()) and bool((out["picks"] == -1).all())
+    info = rep.info()
+    assert info["trajectories"] == 0 and info["empty_samples"] == 1 and info["sample_calls"] == 1 and rep.size() == 0
+    rep.close()
+
+
+def test_sampling_stays_uniform_when_most_of_the_table_is_stale(pkg, torch_cuda):
+    """with a short ring and a long table most table entries point at overwritten rows; draws must still be
+    uniform over the INTACT trajectories (rl_utils.py:126 draws uniformly over what the buffer holds) -- no pile-up on
+    the newest entry"""
+    torch = torch_cuda
+    n, W, ep_len, T = 64, 48, 10, 400
+    rep = pkg.TrajectoryReplay(n_envs=n, obs_dim=6, act_dim=3, window=W, table_cap=8192, kind="reach", seed=5)
+    dev = rep.device
+    rep.begin(torch.zeros((n, 6), device=dev))
+    phase = np.arange(n) % ep_len                                     # envs finish on different rows
+    for k in range(T):
+        d = torch.from_numpy((((k + phase) % ep_len) == ep_len - 1).astype(np.uint8)).to(dev)
+        o = torch.full((n, 6), float(k), device=dev)
+        rep.store(torch.zeros((n, 3), device=dev), torch.zeros(n, device=dev), d, o, o)
+    info = rep.info()
+    ntraj = info["trajectories"]
+    env, start, ln = rep.table(ntraj)
+    now = info["rows"]
+    intact = (start - 1 >= now - W) & (ln > 0)
+    assert intact.sum() >= n * 2 and intact.sum() < 0.2 * ntraj      # most of the table is stale
+    B = 1 << 16
+    picks = rep.sample(B, False, 0.1, 0.8, return_picks=True)["picks"].cpu().numpy()
+    slot = picks[:, 0]
+    assert intact[slot].all()                                         # never a trajectory the ring has overwritten
+    cnt = np.bincount(slot, minlength=ntraj)[intact]
+    mean = B / intact.sum()
+    assert cnt.min() > 0.7 * mean and cnt.max() < 1.3 * mean, (cnt.min(), cnt.max(), mean)
+    assert rep.info()["empty_samples"] == 0
+    rep.close()

@@ -32,9 +32,17 @@ if world > 1:   # first collective = communicator set-up (seconds with 8 ranks):
     if rank == 0:
         print(json.dumps({"nccl_first_collective_s": time.time() - t_init}), flush=True)
 sink = metrics.MetricsSink()
-tr = train.make_trainer(task=task, algo=algo, n_envs=n, device="cuda:%d" % local, seed=0, window=1024, metrics=sink, sync_every=32,
-                        window_episodes=5 * n * world, clip_actions=(os.environ.get("CLIP", "0") == "1"),
-                        noise_std=float(os.environ["NOISE"]) if "NOISE" in os.environ else None)
+# WINDOW = replay ring length in lockstep rows (default 1024 = the last ~2 episode-times; the reference keeps every
+# trajectory of a run: WINDOW >= episode_times * 501 does the same).  UTD = updates per finished env-episode (default:
+# 40 per episode-TIME; UTD=40 is the reference's update-to-data ratio, main.py:209-212).  RATE_WINDOW = episodes per
+# success-rate point (reference: 25).
+window = int(os.environ.get("WINDOW", "1024"))
+utd = float(os.environ["UTD"]) if "UTD" in os.environ else None
+rate_window = int(os.environ["RATE_WINDOW"]) if "RATE_WINDOW" in os.environ else 5 * n * world
+tr = train.make_trainer(task=task, algo=algo, n_envs=n, device="cuda:%d" % local, seed=int(os.environ.get("SEED", "0")), window=window,
+                        metrics=sink, sync_every=int(os.environ.get("SYNC_EVERY", "32")),
+                        window_episodes=rate_window, clip_actions=(os.environ.get("CLIP", "0") == "1"),
+                        noise_std=float(os.environ["NOISE"]) if "NOISE" in os.environ else None, updates_per_episode=utd)
 t0 = time.time()
 chunk = 501
 log = []
@@ -42,7 +50,7 @@ for k in range(episode_times):
     res = tr.run(chunk)
     torch.cuda.synchronize()
     el = time.time() - t0
-    log.append({"episode_time": k + 1, "wall_s": el, "env_steps": res["env_steps"], "updates": res["updates"],
+    log.append({"episode_time": k + 1, "wall_s": el, "env_steps": res["env_steps"], "updates": res["updates"], "episodes": res["episodes"],
                 "success_rate": res["success_rate"], "avg_return": res["avg_return"], "her_ratio": res["her_ratio"]})
     if rank == 0 and ((k + 1) % 5 == 0 or k == 0):
         print(json.dumps(log[-1]), flush=True)
@@ -51,7 +59,8 @@ for k in range(episode_times):
         torch.distributed.all_reduce(stop, op=torch.distributed.ReduceOp.MAX)      # every rank leaves together
     if float(stop) > 0:
         break
-summary = {"task": task, "algo": algo, "n_envs": n, "n_gpus": world, "n_envs_total": n * world, "episode_times": len(log), "wall_s": time.time() - t0,
+summary = {"task": task, "algo": algo, "n_envs": n, "n_gpus": world, "replay_window_rows": window, "updates_per_episode": utd,
+           "noise_std": tr.noise_std, "episodes": log[-1]["episodes"], "updates": log[-1]["updates"], "n_envs_total": n * world, "episode_times": len(log), "wall_s": time.time() - t0,
            "env_steps_per_s_incl_learning": log[-1]["env_steps"] / (time.time() - t0),
            "success_rate_series": sink.series.get("success_rate", []), "log": log}
 if rank == 0:
