@@ -237,13 +237,74 @@ def capture_pool_graphs(torch, envs, actions, steps, stream, first=0):
     return graphs
 
 
-def time_replays(torch, graphs, stream, repeats=REPEATS, spin_s=0.3, barrier=None):
-    """untimed replays for spin_s seconds, then `repeats` replays (round-robin over the graphs), each bracketed by its
-    own event pair on the launching stream; returns the per-replay seconds"""
+def capture_timed_units(torch, envs, actions, steps, stream, first=0):
+    """The headline measurement: CUDA graphs made of timed UNITS laid back to back, one unit = [event record node |
+    exactly K fused-step launches | event record node] (torch.cuda.Event(external=True) records become graph nodes).
+    Inside a graph the units follow each other kernel-to-kernel, so a unit's interval contains K launches and nothing
+    else -- no graph-launch front-end latency, which at K = 20 is ~7 % of a replay timed from outside (measured, first
+    r02 runs) and made the number depend on K.  A graph holds U = clamp(6000 // K, 1, 60) units; as many graphs are
+    captured as it takes to walk the whole pool."""
+    pool, na = len(envs), len(actions)
+    units = max(1, min(60, 6000 // steps))
+    n_graphs = max(1, -(-pool // (units * steps)))
+    graphs = []
+    j = first
+    for g in range(n_graphs):
+        evs = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+               for _ in range(units)]
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=stream):
+            for u in range(units):
+                evs[u][0].record(stream)
+                for _ in range(steps):
+                    envs[j % pool].step(actions[j % na])
+                    j += 1
+                evs[u][1].record(stream)
+        graphs.append((gr, evs))
+    return graphs
+
+
+def time_units(torch, graphs, stream, repeats=REPEATS, spin_s=0.3, barrier=None, refresh=None):
+    """untimed replays for spin_s seconds, then replays until `repeats` unit intervals have been collected (the action
+    ring is redrawn before every replay, see time_replays); returns the per-unit seconds"""
     with torch.cuda.stream(stream):
         t_end = time.time() + spin_s
         i = 0
         while time.time() < t_end:
+            if refresh:
+                refresh()
+            graphs[i % len(graphs)][0].replay()
+            i += 1
+            stream.synchronize()
+    if barrier:
+        barrier()
+    out = []
+    with torch.cuda.stream(stream):
+        while len(out) < repeats:
+            if refresh:
+                refresh()
+            gr, evs = graphs[i % len(graphs)]
+            gr.replay()
+            stream.synchronize()
+            out.extend(a.elapsed_time(b) * 1e-3 for a, b in evs)
+            i += 1
+    if barrier:
+        barrier()
+    return np.array(out[:repeats])
+
+
+def time_replays(torch, graphs, stream, repeats=REPEATS, spin_s=0.3, barrier=None, refresh=None):
+    """untimed replays for spin_s seconds, then `repeats` replays (round-robin over the graphs), each bracketed by its
+    own event pair on the launching stream; returns the per-replay seconds.  `refresh()` runs on the stream before
+    every replay, OUTSIDE the event pairs: it redraws the action ring, so that no env ever sees the same action twice
+    (a captured graph would otherwise hand batch b the same few action sets forever, and arms fed a periodic action
+    sequence drift into a workspace corner where the IK is cheap -- the K = 20 vs K = 2000 gap of the first r02 run)."""
+    with torch.cuda.stream(stream):
+        t_end = time.time() + spin_s
+        i = 0
+        while time.time() < t_end:
+            if refresh:
+                refresh()
             graphs[i % len(graphs)].replay()
             i += 1
             if i % 8 == 0:
@@ -254,6 +315,8 @@ def time_replays(torch, graphs, stream, repeats=REPEATS, spin_s=0.3, barrier=Non
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(repeats)]
     with torch.cuda.stream(stream):
         for r in range(repeats):
+            if refresh:
+                refresh()
             ev[r][0].record(stream)
             graphs[(i + r) % len(graphs)].replay()
             ev[r][1].record(stream)
@@ -300,9 +363,14 @@ def run_ours(args):
         for k in range(max(warmup, 3)):                         # eager warm-up (also first-use init)
             envs[k % pool].step(actions[k % len(actions)])
     stream.synchronize()
-    graphs = capture_pool_graphs(torch, envs, actions, steps, stream, first=max(warmup, 3))
+    try:
+        graphs = capture_timed_units(torch, envs, actions, steps, stream, first=max(warmup, 3))
+        timed_units = True
+    except Exception:          # no external-event support: time whole replays from outside instead
+        graphs = capture_pool_graphs(torch, envs, actions, steps, stream, first=max(warmup, 3))
+        timed_units = False
     cap_launches = sum(e.launch_count for e in envs) - launches0 - max(warmup, 3)
-    assert cap_launches == steps * len(graphs)
+    assert cap_launches % steps == 0
 
     def barrier():
         if world > 1:
@@ -311,10 +379,12 @@ def run_ours(args):
 
     sampler.start()
     # ---- timed region 1: device-resident inputs.  ~0.3 s of untimed replays (clock ramp, mid-episode states), then
-    # REPEATS replays of exactly K launches each, every replay timed by its own event pair, the set bracketed by a
-    # barrier + synchronize; this rank's number is the MEDIAN replay (one ~60 us interval is at the mercy of a single
+    # REPEATS units of exactly K launches each, every unit timed by its own event pair, the set bracketed by a
+    # barrier + synchronize; this rank's number is the MEDIAN unit (one ~60 us interval is at the mercy of a single
     # scheduling hiccup, which is what made round 1's scaling curve read 0.78).
-    times = time_replays(torch, graphs, stream, REPEATS, 0.3, barrier)
+    def redraw():
+        actions.uniform_(-0.7, 0.7, generator=gen)              # fresh U(-0.7,0.7) actions for every replay (untimed)
+    times = (time_units if timed_units else time_replays)(torch, graphs, stream, REPEATS, 0.3, barrier, refresh=redraw)
     sec = float(np.median(times))
     p10, p90 = float(np.percentile(times, 10)), float(np.percentile(times, 90))
     # ---- timed region 2: end to end through the host-buffer C-ABI call.  Every step: the [N,3] f32 actions sit in
@@ -322,25 +392,34 @@ def run_ours(args):
     # host memory and the call returns only when they are readable there (then one value of the result is read).
     e2e_steps = min(steps, args.e2e_steps)
     e2e_pool = min(pool, 64)
-    bufs = []
-    for b in range(e2e_pool):
-        hb = envs[b].host_buffers()
-        hb[0][:] = actions[b % len(actions)].cpu().numpy()
-        bufs.append(hb)
+    bufs = [envs[b].host_buffers() for b in range(e2e_pool)]
+    # the host owns a ring of 509 pre-drawn action sets (prime, ~25 MB) and WRITES the step's actions into the pinned block
+    # every step, like a host-side policy would (the 48 KB memcpy is inside the timed region)
+    host_ring = np.random.default_rng(7 + rank).uniform(-0.7, 0.7, (509, n, 3)).astype(np.float32)
+    kk = 0
     for k in range(max(warmup, 3) + e2e_pool):
-        envs[k % e2e_pool].step_pinned()
+        bufs[kk % e2e_pool][0][:] = host_ring[kk % 509]
+        envs[kk % e2e_pool].step_pinned()
+        kk += 1
     barrier()
     acc = 0.0
     e2e_reps = max(5, min(REPEATS, int(2.0 / max(e2e_steps * 2.5e-5, 1e-6))))     # ~2 s of host stepping at most
     e2e_times = []
-    kk = 0
+    e2e_incl = []
+    clock = time.perf_counter
     for r in range(e2e_reps):
-        t0 = time.perf_counter()
+        t_rep = clock()
+        in_call = 0.0
         for k in range(e2e_steps):
-            rew = envs[kk % e2e_pool].step_pinned()[1]
+            b = kk % e2e_pool
+            bufs[b][0][:] = host_ring[kk % 509]               # the host-side "policy" puts this step's actions into pinned memory
+            t0 = clock()
+            rew = envs[b].step_pinned()[1]                    # the public call: actions cross PCIe, kernel, results cross back
             acc += float(rew[0])                              # the step's result is consumed on the host
+            in_call += clock() - t0
             kk += 1
-        e2e_times.append(time.perf_counter() - t0)
+        e2e_times.append(in_call)
+        e2e_incl.append(clock() - t_rep)
     torch.cuda.synchronize(dev)
     e2e_sec = float(np.median(e2e_times))
     barrier()
@@ -352,15 +431,19 @@ def run_ours(args):
         ea, eb = envs[0], envs[1]
         for k in range(6):
             ea.step_async(); eb.step_async(); ea.step_wait(); eb.step_wait()
+        pipe_steps = max(e2e_steps, 200)
         t0 = time.perf_counter()
+        bufs[0][0][:] = host_ring[kk % 509]; kk += 1
         ea.step_async()
-        for k in range(e2e_steps // 2):
+        for k in range(pipe_steps // 2):
+            bufs[1][0][:] = host_ring[kk % 509]; kk += 1
             eb.step_async()
             acc += float(ea.step_wait()[1][0])
+            bufs[0][0][:] = host_ring[kk % 509]; kk += 1
             ea.step_async()
             acc += float(eb.step_wait()[1][0])
         ea.step_wait()
-        pipe_sec = (time.perf_counter() - t0) / (2 * (e2e_steps // 2) + 1)
+        pipe_sec = (time.perf_counter() - t0) / (2 * (pipe_steps // 2) + 1)
     clocks = sampler.stop()
 
     if world > 1:
@@ -392,11 +475,14 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "rl_%s_env N_envs=%d fused-step kernel, %d x B200 (%d envs total)" % (task, n, world, world * n),
                        "task": task, "n_envs_per_gpu": n, "robot": "kuka_iiwa", "mode": "ik_teleport", "mapping": "lane",
-                       "actions": "pre-generated U(-0.7,0.7) [%d,N,3] f32 on device (launch k uses set k mod %d), auto-reset in kernel" % (N_ACT, N_ACT),
+                       "actions": "U(-0.7,0.7) [%d,N,3] f32 ring on device, launch k uses set k mod %d, the ring is REDRAWN before every "
+                                  "timed replay (outside the event pair): a random walk, no env ever repeats an action; auto-reset in kernel" % (N_ACT, N_ACT),
                        "l2": "inputs larger than L2: round-robin over a pool of %d independent %d-env batches "
                              "(%.0f MB touched state, L2 = 126 MB), every launch HBM-cold" % (pool, n, pool * abytes * n / 1e6),
-                       "launch": "CUDA graphs of exactly K fused-step launches each (%d graphs covering the pool, replayed round-robin), "
-                                 "CUDA event pair per replay on the launching stream" % len(graphs)},
+                       "launch": ("CUDA graphs of timed units, one unit = [event record | exactly K fused-step launches | event record] "
+                                  "(%d graph(s) x %d units covering the pool)" % (len(graphs), len(graphs[0][1]))) if timed_units else
+                                 ("CUDA graphs of exactly K fused-step launches each (%d graphs covering the pool, replayed round-robin), "
+                                  "CUDA event pair per replay on the launching stream" % len(graphs))},
             "timing": {"repeats": REPEATS, "statistic": "median over the timed replays, max over ranks",
                        "p10_ms_per_step": 1e3 * p10 / steps, "p90_ms_per_step": 1e3 * p90 / steps,
                        "e2e_repeats": e2e_reps, "e2e_p10_us_per_step": 1e6 * float(np.percentile(e2e_times, 10)) / e2e_steps,
@@ -410,7 +496,11 @@ def run_ours(args):
                                  "dependent fp32 per 118 B; at N=4096 128 warps on 592 SM sub-partitions wait for the "
                                  "slowest arm's IK (3 DLS iterations typical); see other_configs for the multi-wave sizes"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "ArmSimHandle.step_pinned -> armsim_step_host on the handle's pinned host block "
+                    "steps": e2e_steps, "incl_host_action_write": world * n * e2e_steps / float(np.median(e2e_incl)),
+                    "timed": "time inside the public call + the host read of its result, summed over the K steps of a repeat (median of "
+                             "the repeats); the host-side policy writing the NEXT 48 KB of actions into the pinned block sits between "
+                             "calls and is reported separately (incl_host_action_write)",
+                    "api": "ArmSimHandle.step_pinned -> armsim_step_host on the handle's pinned host block "
                            "(armsim_host_buffers): graph-replayed kernel reads actions / writes results over PCIe, per-block doorbells",
                     "pipelined_depth2": None if pipe_sec is None else
                     {"value": world * n / pipe_sec, "unit": UNIT, "note": "secondary: step_async/step_wait over two independent "
@@ -517,7 +607,11 @@ def side_measurements(torch, pkg, dev, peak_gbs):
                 for j in range(k):
                     envs[j % pool].step(a[j % na])
             # one graph already spans the whole pool here (k >= pool): median of 15 timed replays after 0.25 s untimed
-            tt = time_replays(torch, [g], stream, repeats=15, spin_s=0.25)
+            lim = 30.0 if torque else (0.7 if task == "reach" else 0.4)
+
+            def redraw(a=a, lim=lim):
+                a.uniform_(-lim, lim)
+            tt = time_replays(torch, [g], stream, repeats=15, spin_s=0.25, refresh=redraw)
             sec = float(np.median(tt)) / k
             gbs = ALGO_BYTES[task] * n / sec / 1e9
             res["%s_n%d" % (task, n)] = {"env_steps_per_s": n / sec, "us_per_launch": sec * 1e6, "achieved_gbs": gbs,

@@ -197,7 +197,14 @@ static bool pdl_enabled() {
 // above the 48 KB default, so every such kernel function opts in once.
 template <class F>
 static void ensure_smem(F kern, size_t bytes) {
-  if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  // static + dynamic shared memory above 48 KB needs the opt-in even when the dynamic part alone is below it (torque
+  // kernels: 12 KB static staging + 41.5 KB contact slots), so every kernel with contact slots opts in -- once
+  if (bytes == 0) return;
+  static std::vector<const void*> done;
+  for (const void* p : done)
+    if (p == (const void*)kern) return;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  done.push_back((const void*)kern);
 }
 
 template <class... KArgs, class... Args>
