@@ -239,7 +239,7 @@ def capture_pool_graphs(torch, envs, actions, steps, stream, first=0):
 
 def capture_timed_units(torch, envs, actions, steps, stream, first=0):
     """The headline measurement: CUDA graphs made of timed UNITS laid back to back, one unit = [event record node |
-    exactly K fused-step launches | event record node] (torch.cuda.Event(external=True) records become graph nodes).
+    exactly K fused-step launches | event record node, shared with the next unit] (torch.cuda.Event(external=True) records become graph nodes).
     Inside a graph the units follow each other kernel-to-kernel, so a unit's interval contains K launches and nothing
     else -- no graph-launch front-end latency, which at K = 20 is ~7 % of a replay timed from outside (measured, first
     r02 runs) and made the number depend on K.  A graph holds U = clamp(6000 // K, 1, 60) units; as many graphs are
@@ -250,17 +250,19 @@ def capture_timed_units(torch, envs, actions, steps, stream, first=0):
     graphs = []
     j = first
     for g in range(n_graphs):
-        evs = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
-               for _ in range(units)]
+        # consecutive units SHARE their boundary event: [E0 | K launches | E1 | K launches | E2 ...] -- an interval
+        # E_u -> E_u+1 still holds exactly K launches, but only ONE event node (not two) interrupts the kernel-to-kernel
+        # (programmatic dependent launch) chain per unit, which is what makes K = 20 read like K = 2000
+        marks = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(units + 1)]
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=stream):
+            marks[0].record(stream)
             for u in range(units):
-                evs[u][0].record(stream)
                 for _ in range(steps):
                     envs[j % pool].step(actions[j % na])
                     j += 1
-                evs[u][1].record(stream)
-        graphs.append((gr, evs))
+                marks[u + 1].record(stream)
+        graphs.append((gr, list(zip(marks[:-1], marks[1:]))))
     return graphs
 
 
@@ -517,7 +519,8 @@ def run_ours(args):
     for e in envs:
         e.close()
     if world > 1:
-        dist.destroy_process_group()
+        from drl_on_robot_arm_b200 import distributed as D
+        D.shutdown()
 
 
 def measure_train_updates(torch, dist, dev, world, rank):
@@ -564,6 +567,7 @@ def measure_train_updates(torch, dist, dev, world, rank):
                 same = all(int(g) == int(got[0]) for g in got)
             entry[mode + "_replicas_identical"] = bool(same)
             entry["allreduce_bytes_per_update"] = int(sum(l.bucket.nbytes for l, _ in tr.agent._learners() if l.bucket is not None))
+            tr.release_graphs()             # recorded NCCL work must be gone before the process group is (distributed.shutdown)
             tr.env.close(); tr.replay.close()
             del tr
         out[algo] = entry

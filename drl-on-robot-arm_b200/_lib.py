@@ -9,7 +9,7 @@ import os
 from . import _build
 
 NJ = 7
-ABI_VERSION = 4
+ABI_VERSION = 5
 TASK_REACH, TASK_PUSH, TASK_PICK, TASK_KUKA_REACH = 0, 1, 2, 3
 ROBOT_KUKA_IIWA, ROBOT_DIANA_S1, ROBOT_CUSTOM = 0, 1, 2
 MODE_IK_TELEPORT, MODE_TORQUE = 0, 1
@@ -26,7 +26,7 @@ EXPORTS = [
     "armsim_reset", "armsim_step", "armsim_step_host", "armsim_reset_host", "armsim_set_state", "armsim_get_state",
     "armsim_obs_dim", "armsim_action_dim", "armsim_n_envs", "armsim_mapping", "armsim_launch_count", "armsim_fk_host",
     "armsim_host_buffers", "armsim_step_ex", "armsim_step_host_async", "armsim_step_host_wait",
-    "armsim_explore", "armsim_track_episodes", "armsim_episode_stats", "armsim_set_episode_stats",
+    "armsim_explore", "armsim_policy_act", "armsim_track_episodes", "armsim_episode_stats", "armsim_set_episode_stats",
     "armsim_replay_create", "armsim_replay_destroy", "armsim_replay_begin", "armsim_replay_store", "armsim_replay_sample",
     "armsim_replay_gather", "armsim_replay_info", "armsim_replay_table", "armsim_replay_last_error",
     "armsim_replay_state_bytes", "armsim_replay_get_state", "armsim_replay_set_state",
@@ -95,6 +95,7 @@ def lib():
     L.armsim_step_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.armsim_step_host_async.argtypes = [vp, vp]
     L.armsim_explore.argtypes = [vp, vp, C.c_float, C.c_float, vp, vp]
+    L.armsim_policy_act.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp]
     L.armsim_track_episodes.argtypes = [vp, vp, vp, vp, vp]
     L.armsim_episode_stats.argtypes = [vp, C.POINTER(C.c_double)]
     L.armsim_set_episode_stats.argtypes = [vp, C.POINTER(C.c_double)]

@@ -85,6 +85,11 @@ class _AgentBase:
     def act(self, states):
         raise NotImplementedError
 
+    def acting_policy(self):
+        """the single PolicyNet act() evaluates, or None when acting is more than one MLP forward (double-actor agents
+        pick between two actors by Q value) -- lets the rollout run the forward as one fused launch (env.policy_act)"""
+        return None
+
     def take_action(self, state):
         """reference signature: one state (array [S]) -> action (array [A]) on the host"""
         s = torch.as_tensor(np.asarray(state), dtype=torch.float, device=self.device).view(1, -1)
@@ -143,6 +148,9 @@ class DDPG_MLP(_AgentBase):
     def act(self, states):
         return self.actor(states)
 
+    def acting_policy(self):
+        return self.actor
+
     def train(self, transition_dict, sync=True):
         s, a, r, s2, d = self._batch(transition_dict)
         with torch.no_grad():
@@ -174,6 +182,9 @@ class TD3_MLP(_AgentBase):
     @torch.no_grad()
     def act(self, states):
         return self.actor(states)
+
+    def acting_policy(self):
+        return self.actor
 
     def update_cycle(self):
         return int(self.policy_freq), self.total_it % int(self.policy_freq)      # delayed actor update, TD3_mlp.py:151

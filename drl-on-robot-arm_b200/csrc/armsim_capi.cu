@@ -2,6 +2,7 @@
 // No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -13,6 +14,7 @@
 #include "armsim.h"
 #include "armsim_defaults.h"
 #include "armsim_kernels.cuh"
+#include "policy_kernels.cuh"
 #include "armsim_robot_models.h"
 
 static thread_local char g_err[512] = "";
@@ -289,7 +291,7 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
 
 static int launch_step(ArmSim* s, const float* a, float* o, float* r, uint8_t* d, uint8_t* su, cudaStream_t st,
                        const HostNotify H = HostNotify{nullptr, nullptr}, float* fo = nullptr) {
-  const int grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
+  const int grid = s->grid;
   cudaError_t lerr = cudaSuccess;
   if (s->cfg.mode == ARMSIM_MODE_TORQUE) {
     switch (s->cfg.task * 4 + s->cfg.robot) {
@@ -424,6 +426,8 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   // per-step payload is small enough for PCIe latency, not bandwidth, to dominate; DMA copies beyond that
   s->zero_copy = n <= 65536;
   s->grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
+  // tuning experiment: pad small grids with blocks that own no env (they only ring their doorbell)
+  if (const char* mg = getenv("ARMSIM_MIN_GRID")) s->grid = std::max(s->grid, atoi(mg));
   const size_t flag_bytes = pad((size_t)s->grid * sizeof(unsigned int));
   if (cudaMalloc((void**)&s->d_io, s->act_bytes + s->out_bytes) != cudaSuccess ||
       cudaMalloc((void**)&s->d_stats, 3 * sizeof(unsigned long long)) != cudaSuccess ||
@@ -603,6 +607,27 @@ int armsim_explore(ArmSim* s, const float* actor_out_dev, float noise_std, float
   if (!(noise_std >= 0.0f)) return fail(ARMSIM_E_INVALID, "armsim_explore: noise_std must be >= 0");
   DeviceGuard guard(s->cfg.device);
   explore_kernel<<<s->grid, LANE_BLOCK, 0, (cudaStream_t)stream>>>(s->task, s->S, s->act_dim, actor_out_dev, noise_std, clip, action_out_dev);
+  s->launches += 1;
+  CU(cudaGetLastError());
+  return ARMSIM_OK;
+}
+
+int armsim_policy_act(ArmSim* s, const float* obs_dev, const float* w1, const float* b1, const float* w2, const float* b2,
+                      const float* w3, const float* b3, int32_t hidden, float action_bound, float noise_std, float clip,
+                      float* action_out_dev, void* stream) {
+  if (!s || !obs_dev || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !action_out_dev) return fail(ARMSIM_E_INVALID, "armsim_policy_act: null argument");
+  if (hidden != POLICY_H) return fail(ARMSIM_E_INVALID, "armsim_policy_act: hidden must be %d (got %d)", POLICY_H, hidden);
+  if (s->obs_dim > POLICY_MAX_S || s->act_dim > POLICY_MAX_A) return fail(ARMSIM_E_INVALID, "armsim_policy_act: obs_dim %d / action_dim %d too wide", s->obs_dim, s->act_dim);
+  DeviceGuard guard(s->cfg.device);
+  const PolicyParams P{w1, b1, w2, b2, w3, b3, s->obs_dim, s->act_dim, action_bound};
+  const int grid = (s->n + POLICY_ROWS - 1) / POLICY_ROWS;
+  if (noise_std >= 0.0f) {
+    ensure_smem(policy_mlp_kernel<true>, POLICY_SMEM);
+    policy_mlp_kernel<true><<<grid, POLICY_H, POLICY_SMEM, (cudaStream_t)stream>>>(s->task, s->S, s->n, P, obs_dev, noise_std, clip, action_out_dev);
+  } else {
+    ensure_smem(policy_mlp_kernel<false>, POLICY_SMEM);
+    policy_mlp_kernel<false><<<grid, POLICY_H, POLICY_SMEM, (cudaStream_t)stream>>>(s->task, s->S, s->n, P, obs_dev, 0.f, clip, action_out_dev);
+  }
   s->launches += 1;
   CU(cudaGetLastError());
   return ARMSIM_OK;

@@ -72,6 +72,25 @@ __device__ __forceinline__ void reset_uniforms(const TaskParams& T, unsigned lon
 }
 
 
+// 4 standard normals for (global env id, draw number, block of 4 action components): Philox4x32-10 + Box-Muller.
+// Shared by explore_kernel and the fused policy epilogue, so both draw the same noise.
+__device__ __forceinline__ void explore_normals(const TaskParams& T, unsigned long long gid, unsigned int draw, uint32_t blk,
+                                                float (&z)[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), draw, blk, T.seed_lo ^ 0x4E4F4953u, T.seed_hi, r);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)(r[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-08f;     // (0, 1)
+    const float u2 = (float)(r[2 * h + 1] >> 8) * 5.9604644775390625e-08f;           // [0, 1)
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z[2 * h] = rad * cs;
+    z[2 * h + 1] = rad * sn;
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------------ fast scalar math
 // Single-MUFU forms (<= 2 ulp) without the IEEE slow paths: sqrtf / fdiv expand into a fast path + a CALL to a
 // denormal / rounding fix-up routine, which splits basic blocks (less ILP for ptxas) and bloats the unrolled body.

@@ -452,19 +452,8 @@ explore_kernel(const __grid_constant__ TaskParams T, const StatePtrs S, int act_
   const unsigned int draw = S.explore_count[e];
   S.explore_count[e] = draw + 1u;
   for (int k0 = 0; k0 < act_dim; k0 += 4) {
-    uint32_t r[4];
-    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), draw, (uint32_t)(k0 >> 2), T.seed_lo ^ 0x4E4F4953u, T.seed_hi, r);
     float z[4];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float u1 = ((float)(r[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-08f;     // (0, 1)
-      const float u2 = (float)(r[2 * h + 1] >> 8) * 5.9604644775390625e-08f;           // [0, 1)
-      const float rad = sqrtf(-2.0f * logf(u1));
-      float sn, cs;
-      sincospif(2.0f * u2, &sn, &cs);
-      z[2 * h] = rad * cs;
-      z[2 * h + 1] = rad * sn;
-    }
+    explore_normals(T, gid, draw, (uint32_t)(k0 >> 2), z);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k0 + k < act_dim) {

@@ -9,7 +9,16 @@
 // dt 1/240, gravity -10, damping 0.04, at most 50 projected-Gauss-Seidel sweeps with pybullet's early exit (largest
 // squared velocity residual of a sweep <= 1e-7); pick: fingers close for good within 6 mm and hold by friction only.
 #pragma once
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#define CUBE_FN __device__ __forceinline__
+#define CUBE_STEP_FN static __device__ __noinline__
+#else   // host build of the SAME source (fp32) for tests/cube_host_check.cpp: g++ only, no CUDA
+#include <math.h>
+#define CUBE_FN static inline
+#define CUBE_STEP_FN static inline
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+#endif
 
 namespace cube {
 
@@ -38,9 +47,15 @@ struct State {
   float pos[3], quat[4], v[3], w[3];
 };
 
-__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+CUBE_FN float rcp_approx(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return 1.0f / x;
+#endif
+}
 
-__device__ __forceinline__ void init(State& c, float x, float y, float z, float yaw) {
+CUBE_FN void init(State& c, float x, float y, float z, float yaw) {
   c.pos[0] = x; c.pos[1] = y; c.pos[2] = z;
   float s, co;
   sincosf(0.5f * yaw, &s, &co);
@@ -49,14 +64,14 @@ __device__ __forceinline__ void init(State& c, float x, float y, float z, float 
   for (int i = 0; i < 3; ++i) { c.v[i] = 0.f; c.w[i] = 0.f; }
 }
 
-__device__ __forceinline__ void rot(const float (&q)[4], float (&R)[9]) {
+CUBE_FN void rot(const float (&q)[4], float (&R)[9]) {
   const float x = q[0], y = q[1], z = q[2], w = q[3];
   R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
   R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
   R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
 }
 
-__device__ __forceinline__ void tangents(const float (&n)[3], float (&t1)[3], float (&t2)[3]) {  // btPlaneSpace1
+CUBE_FN void tangents(const float (&n)[3], float (&t1)[3], float (&t2)[3]) {  // btPlaneSpace1
   if (fabsf(n[2]) > 0.70710678f) {
     const float a = n[1] * n[1] + n[2] * n[2], s = rsqrtf(a);
     t1[0] = 0.f; t1[1] = -n[2] * s; t1[2] = n[1] * s;
@@ -70,7 +85,7 @@ __device__ __forceinline__ void tangents(const float (&n)[3], float (&t1)[3], fl
 
 // signed distance sphere <-> box, closest point on the box (relative to the cube centre, world axes) and the unit
 // direction from the sphere towards the cube
-__device__ __forceinline__ float sphere_query(const State& cb, const float (&R)[9], const float (&c)[3], float rad,
+CUBE_FN float sphere_query(const State& cb, const float (&R)[9], const float (&c)[3], float rad,
                                               float (&rrel)[3], float (&n)[3]) {
   const float d[3] = {c[0] - cb.pos[0], c[1] - cb.pos[1], c[2] - cb.pos[2]};
   float l[3], cl[3], nl[3];
@@ -115,14 +130,14 @@ __device__ __forceinline__ float sphere_query(const State& cb, const float (&R)[
 // pick: palm + two fingers whose tips sit TIP_OPEN / TIP_CLOSED off the axis.
 struct Capsule { float a[3], b[3], rad; };
 
-__device__ __forceinline__ void axis_point(const float (&ee)[3], const float (&Ree)[9], float along, float side, float (&o)[3]) {
+CUBE_FN void axis_point(const float (&ee)[3], const float (&Ree)[9], float along, float side, float (&o)[3]) {
   o[0] = fmaf(side, Ree[0], fmaf(along, Ree[2], ee[0]));
   o[1] = fmaf(side, Ree[3], fmaf(along, Ree[5], ee[1]));
   o[2] = fmaf(side, Ree[6], fmaf(along, Ree[8], ee[2]));
 }
 
 template <bool PICK>
-__device__ __forceinline__ void arm_capsule(const float (&ee)[3], const float (&Ree)[9], float grip, int p, Capsule& k) {
+CUBE_FN void arm_capsule(const float (&ee)[3], const float (&Ree)[9], float grip, int p, Capsule& k) {
   if (!PICK) {
     axis_point(ee, Ree, PUSH_A0, 0.f, k.a); axis_point(ee, Ree, PUSH_A1, 0.f, k.b); k.rad = PUSH_R;
   } else if (p == 0) {
@@ -135,7 +150,7 @@ __device__ __forceinline__ void arm_capsule(const float (&ee)[3], const float (&
 }
 
 // capsule <-> box: the sphere of the capsule's radius at the axis point nearest the cube centre
-__device__ __forceinline__ float capsule_query(const State& cb, const float (&R)[9], const Capsule& k, float (&rrel)[3], float (&n)[3]) {
+CUBE_FN float capsule_query(const State& cb, const float (&R)[9], const Capsule& k, float (&rrel)[3], float (&n)[3]) {
   const float ab[3] = {k.b[0] - k.a[0], k.b[1] - k.a[1], k.b[2] - k.a[2]};
   const float ac[3] = {cb.pos[0] - k.a[0], cb.pos[1] - k.a[1], cb.pos[2] - k.a[2]};
   const float len2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
@@ -146,7 +161,7 @@ __device__ __forceinline__ float capsule_query(const State& cb, const float (&R)
 }
 
 // getClosestPoints(kuka, cube, 0.006) stand-in (rl_pick_env.py:412): min signed distance capsule <-> cube
-__device__ __forceinline__ float gripper_distance(const State& cb, const float (&ee)[3], const float (&Ree)[9], float grip) {
+CUBE_FN float gripper_distance(const State& cb, const float (&ee)[3], const float (&Ree)[9], float grip) {
   float R[9], rr[3], nn[3];
   rot(cb.quat, R);
   float best = 1e30f;
@@ -159,181 +174,297 @@ __device__ __forceinline__ float gripper_distance(const State& cb, const float (
   return best;
 }
 
-// ---- per-thread contact slots in shared memory ---------------------------------------------------------------------
-// The contacts of the oracle's list live in a per-thread column of dynamic shared memory: word k of the calling thread
-// is scratch[k * SLOT_STRIDE + threadIdx.x] (conflict-free: a warp reads 32 consecutive words).  Corner / plane
-// contacts are compacted per lane into slots 0..nc-1 (corner order = the oracle's Gauss-Seidel order, at most a face),
-// the capsule contacts have static slots with an "active" bit.  Everything that does not change during the sweeps --
-// lever arms, r x dir, the row's effective mass k and 1/k -- is computed once per step, so a row inside the sweep loop
-// is LDS + one 6-term dot + clamp + two 3-term AXPYs; the cube's twist stays in registers.
-// (Round 1 history: a compacted, dynamically indexed contact array lived in local memory, ~170 instructions per
-// contact per sweep; static slots in registers made ptxas rematerialise the corner geometry inside the sweep loop,
-// ~70-85; the shared-memory slots are ~50.)
+
+// ---- the contact solve ---------------------------------------------------------------------------------------------
+// Same contact list and the same projected-Gauss-Seidel ROW ORDER as oracle/cube_model.h (corner contacts compacted in
+// corner order into 4 slots, then the arm capsules; each contact = normal, t1, t2), the same clamps and the same early
+// exit -- but arranged for the latency of ONE lane, because at the BASELINE sizes (push 4096, pick 2048: a single
+// wave) a launch lasts as long as its slowest cube, and a cube squeezed between a capsule and the table runs all 50
+// sweeps:
+//
+//  * fixed row slots, absent rows masked: every lane runs the same straight-line sweep over 4 corner slots + the
+//    capsules; a slot without a contact has 1/k = 0, so its row leaves impulse and twist untouched (bit-exactly), and
+//    capsule blocks no lane of the warp needs are skipped warp-uniformly.  No dynamic indexing, no loads that depend on
+//    the solve: every row constant sits at a static per-thread shared-memory address and is fetched off the chain.
+//  * three-row look-ahead.  Row i of Gauss-Seidel needs J_i . u with u = the twist after row i-1, a 10-operation
+//    dependent chain per row (dot, bias, clamp, impulse difference, twist update) that nothing can overlap.  Since
+//    u_(i-1) = u_(i-3) + U_(i-2) dl_(i-2) + U_(i-1) dl_(i-1)  (U_j = M^-1 J_j^T),
+//        J_i . u_(i-1) = J_i . u_(i-3) + B_(i,i-2) dl_(i-2) + B_(i,i-1) dl_(i-1),      B_(i,j) = J_i . U_j
+//    the dot product runs on the twist of three rows ago -- off the critical path -- and the two Delassus entries
+//    B (times 1/k_i: c2, c1) are computed once per sim step.  Left on the chain: one FMA, the clamp, one subtraction
+//    (4 operations per row instead of 10).  Algebraically identical to the oracle's update, rounding differs at 1e-7.
+//
+// Per-thread column of dynamic shared memory: word k of the calling thread is scratch[k * SLOT_STRIDE + threadIdx.x]
+// (conflict-free).  The accumulated impulses and the twist history live in registers.
+#if defined(__CUDACC__)
 constexpr int SLOT_STRIDE = 128;                 // = LANE_BLOCK (threads per block of every kernel that steps cubes)
-constexpr int CORNER_WORDS = 13;                 // r[3], bias, k n/t1/t2, 1/k n/t1/t2, lambda n/t1/t2
-constexpr int ROW_WORDS = 9;                     // dir[3], r x dir [3], k, 1/k, lambda
-constexpr int PROXY_WORDS = 3 * ROW_WORDS + 1;   // rows n, t1, t2 + bias
+#else
+constexpr int SLOT_STRIDE = 1;
+#endif
+constexpr int CORNER_WORDS = 16;                 // r[3], k n/t1/t2, 1/k n/t1/t2, c1 n/t1/t2, c2 n/t1/t2, h
+constexpr int ROW_WORDS = 10;                    // dir[3], r x dir [3], k, 1/k, c1, c2
+constexpr int PROXY_WORDS = 3 * ROW_WORDS + 1;   // rows n, t1, t2 + h
 template <bool PICK> constexpr int scratch_words() { return MAX_CORNERS * CORNER_WORDS + (PICK ? 3 : 1) * PROXY_WORDS; }
-template <bool PICK> constexpr int scratch_bytes() { return scratch_words<PICK>() * SLOT_STRIDE * 4; }   // push 40 KB, pick 68 KB
+template <bool PICK> constexpr int scratch_bytes() { return scratch_words<PICK>() * SLOT_STRIDE * 4; }   // push 47.5 KB, pick 78.5 KB
 
+#if defined(__CUDACC__)
 extern __shared__ float cube_scratch[];
+CUBE_FN float* scratch_column() { return cube_scratch + threadIdx.x; }
+CUBE_FN bool warp_any(bool p) { return __any_sync(__activemask(), p) != 0; }
+#else
+static float cube_scratch_host[MAX_CORNERS * CORNER_WORDS + 3 * PROXY_WORDS];
+CUBE_FN float* scratch_column() { return cube_scratch_host; }
+CUBE_FN bool warp_any(bool p) { return p; }
+#endif
 
-// One projected-Gauss-Seidel row from its slot; v, w = cube twist (registers); res = running max of the squared
-// velocity change along a row (Bullet: deltaImpulse / jacDiagABInv, squared).
-__device__ __forceinline__ float slot_row(float* s, float (&v)[3], float (&w)[3], float target, float lo, float hi, float& res) {
-  const float d0 = s[0 * SLOT_STRIDE], d1 = s[1 * SLOT_STRIDE], d2 = s[2 * SLOT_STRIDE];
-  const float x0 = s[3 * SLOT_STRIDE], x1 = s[4 * SLOT_STRIDE], x2 = s[5 * SLOT_STRIDE];
-  const float k = s[6 * SLOT_STRIDE], ik = s[7 * SLOT_STRIDE], acc = s[8 * SLOT_STRIDE];
-  const float vrel = fmaf(d0, v[0], fmaf(d1, v[1], d2 * v[2])) + fmaf(x0, w[0], fmaf(x1, w[1], x2 * w[2]));
-  const float nl = fminf(fmaxf(fmaf(target - vrel, ik, acc), lo), hi);
-  const float dl = nl - acc;
-  s[8 * SLOT_STRIDE] = nl;
+struct Twist { float v[3], w[3]; };
+// a = twist after row i-3, b = after row i-2, c = after row i-1; d1 = impulse change of row i-1, d2 = of row i-2
+struct History { Twist a, b, c; float d1, d2; };
+
+CUBE_FN void advance(History& H, const Twist& un, float dl) {
+  H.a = H.b; H.b = H.c; H.c = un;
+  H.d2 = H.d1; H.d1 = dl;
+}
+
+// Delassus entry between two rows given as explicit 6-vectors (dir, r x dir): J_a . M^-1 J_b^T  (INV_MASS = 1)
+CUBE_FN float delassus(const float (&a)[6], const float (&b)[6]) {
+  const float lin = fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0]));
+  const float ang = fmaf(a[5], b[5], fmaf(a[4], b[4], a[3] * b[3]));
+  return fmaf(ang, INV_INERTIA, lin);
+}
+
+// The new accumulated impulse of a row: clamp(lam + (target - J.u_(i-1)) / k) in the look-ahead form; jv = J . u_(i-3),
+// lamh = lam + target / k.  On the dependent chain: the last FMA and the clamp.
+CUBE_FN float row_impulse(float jv, float ik, float c1, float c2, float lamh, const History& H) {
+  float g = fmaf(-ik, jv, lamh);
+  g = fmaf(-c2, H.d2, g);
+  return fmaf(-c1, H.d1, g);
+}
+
+// The three rows of corner slot c.  The plane normal is +z, for which btPlaneSpace1 (tangents()) gives t1 = (0,-1,0),
+// t2 = (1,0,0): J_n = (0,0,1, r1,-r0,0), J_t1 = (0,-1,0, r2,0,-r0), J_t2 = (1,0,0, 0,r2,-r1).
+CUBE_FN void corner_rows(const float* c, float (&lam)[3], History& H, float& res) {
+  constexpr int S = SLOT_STRIDE;
+  const float r0 = c[0], r1 = c[1 * S], r2 = c[2 * S];
+  {  // normal
+    const float jv = fmaf(r1, H.a.w[0], fmaf(-r0, H.a.w[1], H.a.v[2]));
+    const float nl = fmaxf(row_impulse(jv, c[6 * S], c[9 * S], c[12 * S], lam[0] + c[15 * S], H), 0.0f);
+    const float dl = nl - lam[0];
+    lam[0] = nl;
+    const float dli = dl * INV_INERTIA;
+    Twist un = H.c;
+    un.v[2] += dl;
+    un.w[0] = fmaf(dli, r1, un.w[0]);
+    un.w[1] = fmaf(-dli, r0, un.w[1]);
+    const float dv = dl * c[3 * S];
+    res = fmaxf(res, dv * dv);
+    advance(H, un, dl);
+  }
+  const float lim = MU * lam[0];
+  {  // t1
+    const float jv = fmaf(r2, H.a.w[0], fmaf(-r0, H.a.w[2], -H.a.v[1]));
+    const float nl = fminf(fmaxf(row_impulse(jv, c[7 * S], c[10 * S], c[13 * S], lam[1], H), -lim), lim);
+    const float dl = nl - lam[1];
+    lam[1] = nl;
+    const float dli = dl * INV_INERTIA;
+    Twist un = H.c;
+    un.v[1] -= dl;
+    un.w[0] = fmaf(dli, r2, un.w[0]);
+    un.w[2] = fmaf(-dli, r0, un.w[2]);
+    const float dv = dl * c[4 * S];
+    res = fmaxf(res, dv * dv);
+    advance(H, un, dl);
+  }
+  {  // t2
+    const float jv = fmaf(r2, H.a.w[1], fmaf(-r1, H.a.w[2], H.a.v[0]));
+    const float nl = fminf(fmaxf(row_impulse(jv, c[8 * S], c[11 * S], c[14 * S], lam[2], H), -lim), lim);
+    const float dl = nl - lam[2];
+    lam[2] = nl;
+    const float dli = dl * INV_INERTIA;
+    Twist un = H.c;
+    un.v[0] += dl;
+    un.w[1] = fmaf(dli, r2, un.w[1]);
+    un.w[2] = fmaf(-dli, r1, un.w[2]);
+    const float dv = dl * c[5 * S];
+    res = fmaxf(res, dv * dv);
+    advance(H, un, dl);
+  }
+}
+
+// One row of a capsule contact from its slot q (dir, r x dir, k, 1/k, c1, c2)
+CUBE_FN void capsule_row(const float* q, float& lam, float lamh, float lo, float hi, History& H, float& res) {
+  constexpr int S = SLOT_STRIDE;
+  const float d0 = q[0], d1 = q[1 * S], d2 = q[2 * S], x0 = q[3 * S], x1 = q[4 * S], x2 = q[5 * S];
+  const float jv = fmaf(d0, H.a.v[0], fmaf(d1, H.a.v[1], d2 * H.a.v[2])) + fmaf(x0, H.a.w[0], fmaf(x1, H.a.w[1], x2 * H.a.w[2]));
+  const float nl = fminf(fmaxf(row_impulse(jv, q[7 * S], q[8 * S], q[9 * S], lamh, H), lo), hi);
+  const float dl = nl - lam;
+  lam = nl;
   const float dli = dl * INV_INERTIA;
-  v[0] = fmaf(dl, d0, v[0]); v[1] = fmaf(dl, d1, v[1]); v[2] = fmaf(dl, d2, v[2]);      // INV_MASS = 1
-  w[0] = fmaf(dli, x0, w[0]); w[1] = fmaf(dli, x1, w[1]); w[2] = fmaf(dli, x2, w[2]);
-  const float dv = dl * k;
+  Twist un = H.c;
+  un.v[0] = fmaf(dl, d0, un.v[0]); un.v[1] = fmaf(dl, d1, un.v[1]); un.v[2] = fmaf(dl, d2, un.v[2]);      // INV_MASS = 1
+  un.w[0] = fmaf(dli, x0, un.w[0]); un.w[1] = fmaf(dli, x1, un.w[1]); un.w[2] = fmaf(dli, x2, un.w[2]);
+  const float dv = dl * q[6 * S];
   res = fmaxf(res, dv * dv);
-  return nl;
+  advance(H, un, dl);
 }
 
-// The three rows of a cube-corner / plane contact.  The plane normal is +z, for which btPlaneSpace1 (tangents()) gives
-// t1 = (0,-1,0), t2 = (1,0,0); r x dir is then a signed permutation of r and the generic row collapses to a handful
-// of FMAs.  k* = 1/m + |r x dir|^2 / I per row and ik* = 1 / k*, computed once per step.
-__device__ __forceinline__ void table_rows(float (&v)[3], float (&w)[3], float r0, float r1, float r2, float bias, float kn,
-                                           float k1, float k2, float ikn, float ik1, float ik2, float& ln, float& l1, float& l2,
-                                           float& res) {
-  const float r0i = r0 * INV_INERTIA, r1i = r1 * INV_INERTIA, r2i = r2 * INV_INERTIA;
-  {  // normal (0,0,1): r x n = (r1, -r0, 0)
-    const float vrel = fmaf(r1, w[0], fmaf(-r0, w[1], v[2]));
-    const float nl = fmaxf(fmaf(bias - vrel, ikn, ln), 0.0f);
-    const float dl = nl - ln;
-    ln = nl;
-    v[2] += dl;
-    w[0] = fmaf(dl, r1i, w[0]);
-    w[1] = fmaf(-dl, r0i, w[1]);
-    const float dv = dl * kn;
-    res = fmaxf(res, dv * dv);
-  }
-  const float lim = MU * ln;
-  {  // t1 = (0,-1,0): r x t1 = (r2, 0, -r0)
-    const float vrel = fmaf(r2, w[0], fmaf(-r0, w[2], -v[1]));
-    const float nl = fminf(fmaxf(fmaf(-vrel, ik1, l1), -lim), lim);
-    const float dl = nl - l1;
-    l1 = nl;
-    v[1] -= dl;
-    w[0] = fmaf(dl, r2i, w[0]);
-    w[2] = fmaf(-dl, r0i, w[2]);
-    const float dv = dl * k1;
-    res = fmaxf(res, dv * dv);
-  }
-  {  // t2 = (1,0,0): r x t2 = (0, r2, -r1)
-    const float vrel = fmaf(r2, w[1], fmaf(-r1, w[2], v[0]));
-    const float nl = fminf(fmaxf(fmaf(-vrel, ik2, l2), -lim), lim);
-    const float dl = nl - l2;
-    l2 = nl;
-    v[0] += dl;
-    w[1] = fmaf(dl, r2i, w[1]);
-    w[2] = fmaf(-dl, r1i, w[2]);
-    const float dv = dl * k2;
-    res = fmaxf(res, dv * dv);
-  }
+// explicit 6-vectors of a corner slot's t1 / t2 / n rows (set-up only)
+CUBE_FN void corner_J(const float (&r)[3], float (&jn)[6], float (&j1)[6], float (&j2)[6]) {
+  jn[0] = 0.f; jn[1] = 0.f;  jn[2] = 1.f; jn[3] = r[1]; jn[4] = -r[0]; jn[5] = 0.f;
+  j1[0] = 0.f; j1[1] = -1.f; j1[2] = 0.f; j1[3] = r[2]; j1[4] = 0.f;   j1[5] = -r[0];
+  j2[0] = 1.f; j2[1] = 0.f;  j2[2] = 0.f; j2[3] = 0.f;  j2[4] = r[2];  j2[5] = -r[1];
 }
 
-// one p.stepSimulation() for the cube; grip: 0 open / push, >= 0.5 fingers closed.  Same contact list and the same
-// Gauss-Seidel order as oracle/cube_model.h (corner contacts in corner order, then the arm capsules).  Needs
-// scratch_bytes<PICK>() of dynamic shared memory in the calling kernel.
+// one p.stepSimulation() for the cube; grip: 0 open / push, >= 0.5 fingers closed.  Needs scratch_bytes<PICK>() of
+// dynamic shared memory in the calling kernel.
 template <bool PICK>
-static __device__ __noinline__ void step(State& cbm, const float (&ee)[3], const float (&Ree)[9], float grip) {
+CUBE_STEP_FN void step(State& cbm, const float (&ee)[3], const float (&Ree)[9], float grip) {
+  constexpr int S = SLOT_STRIDE;
+  constexpr int NP = PICK ? 3 : 1;
   State cb = cbm;                    // work on a register copy (the caller's object lives behind a reference)
-  float v[3], w[3];
+  History H;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { v[i] = cb.v[i] * DAMP; w[i] = cb.w[i] * DAMP; }
-  v[2] = (cb.v[2] - G * DT) * DAMP;
+  for (int i = 0; i < 3; ++i) { H.c.v[i] = cb.v[i] * DAMP; H.c.w[i] = cb.w[i] * DAMP; }
+  H.c.v[2] = (cb.v[2] - G * DT) * DAMP;
+  H.a = H.c; H.b = H.c;
+  H.d1 = 0.f; H.d2 = 0.f;
 
-  float* const sm = cube_scratch + threadIdx.x;
+  float* const sm = scratch_column();
   float R[9];
   rot(cb.quat, R);
-  unsigned active = 0u;               // bit p : arm capsule p in contact
-  int nc = 0;                         // corner contacts, compacted in corner order into slots 0 .. nc-1
+  // ---- corner / plane contacts: compacted in corner order into slots 0 .. nc-1 (r and the bias, through the slots)
+  int nc = 0;
   {
     const bool on_table = cb.pos[0] >= TABLE_X0 && cb.pos[0] <= TABLE_X1 && cb.pos[1] >= TABLE_Y0 && cb.pos[1] <= TABLE_Y1;
     const float plane_z = on_table ? TABLE_Z : GROUND_Z;
-    float H[9];                      // half-edge vectors: column k of R times HALF
+    float Hh[9];                     // half-edge vectors: column k of R times HALF
 #pragma unroll
-    for (int i = 0; i < 9; ++i) H[i] = R[i] * HALF;
+    for (int i = 0; i < 9; ++i) Hh[i] = R[i] * HALF;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       float r[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i)
-        r[i] = ((c & 1) ? H[3 * i] : -H[3 * i]) + ((c & 2) ? H[3 * i + 1] : -H[3 * i + 1]) + ((c & 4) ? H[3 * i + 2] : -H[3 * i + 2]);
+        r[i] = ((c & 1) ? Hh[3 * i] : -Hh[3 * i]) + ((c & 2) ? Hh[3 * i + 1] : -Hh[3 * i + 1]) + ((c & 4) ? Hh[3 * i + 2] : -Hh[3 * i + 2]);
       const float gap = cb.pos[2] + r[2] - plane_z;
       if (gap < MARGIN && nc < MAX_CORNERS) {
-        float* s = sm + nc * (CORNER_WORDS * SLOT_STRIDE);
+        float* s = sm + nc * (CORNER_WORDS * S);
         ++nc;
-        const float a = r[0] * r[0], b = r[1] * r[1], d = r[2] * r[2];
-        const float kn = fmaf(a + b, INV_INERTIA, INV_MASS), k1 = fmaf(d + a, INV_INERTIA, INV_MASS), k2 = fmaf(d + b, INV_INERTIA, INV_MASS);
-        s[0 * SLOT_STRIDE] = r[0]; s[1 * SLOT_STRIDE] = r[1]; s[2 * SLOT_STRIDE] = r[2];
-        s[3 * SLOT_STRIDE] = gap < 0.f ? -ERP * gap * INV_DT : -gap * INV_DT;
-        s[4 * SLOT_STRIDE] = kn; s[5 * SLOT_STRIDE] = k1; s[6 * SLOT_STRIDE] = k2;
-        s[7 * SLOT_STRIDE] = rcp_approx(kn); s[8 * SLOT_STRIDE] = rcp_approx(k1); s[9 * SLOT_STRIDE] = rcp_approx(k2);
-        s[10 * SLOT_STRIDE] = 0.f; s[11 * SLOT_STRIDE] = 0.f; s[12 * SLOT_STRIDE] = 0.f;
+        s[0] = r[0]; s[1 * S] = r[1]; s[2 * S] = r[2];
+        s[15 * S] = gap < 0.f ? -ERP * gap * INV_DT : -gap * INV_DT;      // the bias; becomes h = bias / k below
       }
     }
   }
-  constexpr int NP = PICK ? 3 : 1;
-  {
+  float rc[MAX_CORNERS][3], bias[MAX_CORNERS];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      Capsule cap;
-      arm_capsule<PICK>(ee, Ree, grip, p, cap);
-      float rr[3], dir[3][3];
-      const float d = capsule_query(cb, R, cap, rr, dir[0]);
-      if (d < 0.f) {
-        active |= 1u << p;
-        tangents(dir[0], dir[1], dir[2]);
-        float* s = sm + (MAX_CORNERS * CORNER_WORDS + p * PROXY_WORDS) * SLOT_STRIDE;
+  for (int c = 0; c < MAX_CORNERS; ++c) {
+    const float* s = sm + c * (CORNER_WORDS * S);
+    const bool present = c < nc;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          float* q = s + k * (ROW_WORDS * SLOT_STRIDE);
-          const float x0 = rr[1] * dir[k][2] - rr[2] * dir[k][1], x1 = rr[2] * dir[k][0] - rr[0] * dir[k][2],
-                      x2 = rr[0] * dir[k][1] - rr[1] * dir[k][0];
-          const float kk = fmaf(x0 * x0 + x1 * x1 + x2 * x2, INV_INERTIA, INV_MASS);
-          q[0 * SLOT_STRIDE] = dir[k][0]; q[1 * SLOT_STRIDE] = dir[k][1]; q[2 * SLOT_STRIDE] = dir[k][2];
-          q[3 * SLOT_STRIDE] = x0; q[4 * SLOT_STRIDE] = x1; q[5 * SLOT_STRIDE] = x2;
-          q[6 * SLOT_STRIDE] = kk; q[7 * SLOT_STRIDE] = rcp_approx(kk); q[8 * SLOT_STRIDE] = 0.f;
-        }
-        s[3 * ROW_WORDS * SLOT_STRIDE] = -ERP * d * INV_DT;
-      }
+    for (int i = 0; i < 3; ++i) rc[c][i] = present ? s[i * S] : 0.f;
+    bias[c] = present ? s[15 * S] : 0.f;
+  }
+  // ---- arm capsules: rows into their slots; prev1 / prev2 = explicit t1 / t2 rows of the block before (GS order)
+  float prev1[6], prev2[6], scratch_n[6];
+  corner_J(rc[MAX_CORNERS - 1], scratch_n, prev1, prev2);
+  unsigned active = 0u;               // bit p : arm capsule p in contact
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    Capsule cap;
+    arm_capsule<PICK>(ee, Ree, grip, p, cap);
+    float rr[3], dir[3][3];
+    const float d = capsule_query(cb, R, cap, rr, dir[0]);
+    const bool on = d < 0.f;
+    if (on) active |= 1u << p;
+    tangents(dir[0], dir[1], dir[2]);
+    float J[3][6], kk[3], ik[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      J[k][0] = on ? dir[k][0] : 0.f; J[k][1] = on ? dir[k][1] : 0.f; J[k][2] = on ? dir[k][2] : 0.f;
+      J[k][3] = on ? rr[1] * dir[k][2] - rr[2] * dir[k][1] : 0.f;
+      J[k][4] = on ? rr[2] * dir[k][0] - rr[0] * dir[k][2] : 0.f;
+      J[k][5] = on ? rr[0] * dir[k][1] - rr[1] * dir[k][0] : 0.f;
+      const float k0 = fmaf(J[k][3] * J[k][3] + J[k][4] * J[k][4] + J[k][5] * J[k][5], INV_INERTIA, INV_MASS);
+      kk[k] = on ? k0 : 0.f;
+      ik[k] = on ? rcp_approx(k0) : 0.f;
     }
+    const float c1[3] = {ik[0] * delassus(J[0], prev2), ik[1] * delassus(J[1], J[0]), ik[2] * delassus(J[2], J[1])};
+    const float c2[3] = {ik[0] * delassus(J[0], prev1), ik[1] * delassus(J[1], prev2), ik[2] * delassus(J[2], J[0])};
+    float* s = sm + (MAX_CORNERS * CORNER_WORDS + p * PROXY_WORDS) * S;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float* q = s + k * (ROW_WORDS * S);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) q[i * S] = J[k][i];
+      q[6 * S] = kk[k]; q[7 * S] = ik[k]; q[8 * S] = c1[k]; q[9 * S] = c2[k];
+    }
+    s[3 * ROW_WORDS * S] = on ? ik[0] * (-ERP * d * INV_DT) : 0.f;          // h = target / k of the normal row
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { prev1[i] = J[1][i]; prev2[i] = J[2][i]; }
+  }
+  // ---- corner slots: effective masses and the look-ahead couplings (closed forms for a +z normal)
+#pragma unroll
+  for (int c = 0; c < MAX_CORNERS; ++c) {
+    const bool present = c < nc;
+    const float r0 = rc[c][0], r1 = rc[c][1], r2 = rc[c][2];
+    const float a = r0 * r0, b = r1 * r1, d = r2 * r2;
+    const float kn = fmaf(a + b, INV_INERTIA, INV_MASS), k1 = fmaf(d + a, INV_INERTIA, INV_MASS), k2 = fmaf(d + b, INV_INERTIA, INV_MASS);
+    const float ikn = present ? rcp_approx(kn) : 0.f, ik1 = present ? rcp_approx(k1) : 0.f, ik2 = present ? rcp_approx(k2) : 0.f;
+    float bn2, bn1, b12;              // B(n, prev t2), B(n, prev t1), B(t1, prev t2)
+    if (c == 0) {                     // the block before slot 0 is the last capsule (previous sweep)
+      float jn[6], j1[6], j2[6];
+      corner_J(rc[0], jn, j1, j2);
+      bn2 = delassus(jn, prev2); bn1 = delassus(jn, prev1); b12 = delassus(j1, prev2);
+    } else {
+      const float p1 = rc[c - 1][1], p2 = rc[c - 1][2];
+      bn2 = -INV_INERTIA * r0 * p2; bn1 = INV_INERTIA * r1 * p2; b12 = INV_INERTIA * r0 * p1;
+    }
+    float* s = sm + c * (CORNER_WORDS * S);
+    s[3 * S] = present ? kn : 0.f; s[4 * S] = present ? k1 : 0.f; s[5 * S] = present ? k2 : 0.f;
+    s[6 * S] = ikn; s[7 * S] = ik1; s[8 * S] = ik2;
+    s[9 * S] = ikn * bn2;                           // c1: coupling with the row before
+    s[10 * S] = ik1 * (INV_INERTIA * r1 * r2);      //     B(t1, n)
+    s[11 * S] = ik2 * (INV_INERTIA * r0 * r1);      //     B(t2, t1)
+    s[12 * S] = ikn * bn1;                          // c2: coupling with the row two before
+    s[13 * S] = ik1 * b12;
+    s[14 * S] = ik2 * (-INV_INERTIA * r0 * r2);     //     B(t2, n)
+    s[15 * S] = ikn * bias[c];
+    if (!present) { s[0] = 0.f; s[1 * S] = 0.f; s[2 * S] = 0.f; }
   }
 
-  // Sweeps: every lane stops at ITS OWN convergence (pybullet's residual test) or after 50; a warp runs as long as its
-  // slowest cube (resting cubes take ~7 sweeps, cubes squeezed between a capsule and the table all 50).
+  // ---- sweeps: every lane stops at ITS OWN convergence (pybullet's residual test) or after 50; a warp runs as long
+  // as its slowest cube (resting cubes take ~7 sweeps, cubes squeezed between a capsule and the table all 50)
+  float lam[MAX_CORNERS][3], lamc[NP][3];
+#pragma unroll
+  for (int c = 0; c < MAX_CORNERS; ++c) { lam[c][0] = 0.f; lam[c][1] = 0.f; lam[c][2] = 0.f; }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) { lamc[p][0] = 0.f; lamc[p][1] = 0.f; lamc[p][2] = 0.f; }
+  bool any_cap[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) any_cap[p] = warp_any((active >> p) & 1u);
   bool act = (active | (unsigned)nc) != 0u;
 #pragma unroll 1
   for (int it = 0; act && it < PGS_ITERS; ++it) {
     float res = 0.f;
-#pragma unroll 1
-    for (int j = 0; j < nc; ++j) {
-      float* s = sm + j * (CORNER_WORDS * SLOT_STRIDE);
-      float ln = s[10 * SLOT_STRIDE], l1 = s[11 * SLOT_STRIDE], l2 = s[12 * SLOT_STRIDE];
-      table_rows(v, w, s[0 * SLOT_STRIDE], s[1 * SLOT_STRIDE], s[2 * SLOT_STRIDE], s[3 * SLOT_STRIDE], s[4 * SLOT_STRIDE],
-                 s[5 * SLOT_STRIDE], s[6 * SLOT_STRIDE], s[7 * SLOT_STRIDE], s[8 * SLOT_STRIDE], s[9 * SLOT_STRIDE], ln, l1, l2, res);
-      s[10 * SLOT_STRIDE] = ln; s[11 * SLOT_STRIDE] = l1; s[12 * SLOT_STRIDE] = l2;
-    }
+#pragma unroll
+    for (int c = 0; c < MAX_CORNERS; ++c) corner_rows(sm + c * (CORNER_WORDS * S), lam[c], H, res);
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      if (active & (1u << p)) {
-        float* s = sm + (MAX_CORNERS * CORNER_WORDS + p * PROXY_WORDS) * SLOT_STRIDE;
-        const float ln = slot_row(s, v, w, s[3 * ROW_WORDS * SLOT_STRIDE], 0.0f, 1e30f, res);
-        const float lim = MU * ln;
-        slot_row(s + ROW_WORDS * SLOT_STRIDE, v, w, 0.0f, -lim, lim, res);
-        slot_row(s + 2 * ROW_WORDS * SLOT_STRIDE, v, w, 0.0f, -lim, lim, res);
+      if (any_cap[p]) {
+        const float* s = sm + (MAX_CORNERS * CORNER_WORDS + p * PROXY_WORDS) * S;
+        capsule_row(s, lamc[p][0], lamc[p][0] + s[3 * ROW_WORDS * S], 0.0f, 1e30f, H, res);
+        const float lim = MU * lamc[p][0];
+        capsule_row(s + ROW_WORDS * S, lamc[p][1], lamc[p][1], -lim, lim, H, res);
+        capsule_row(s + 2 * ROW_WORDS * S, lamc[p][2], lamc[p][2], -lim, lim, H, res);
+      } else {                        // three rows that change nothing: the history collapses onto the current twist
+        H.a = H.c; H.b = H.c;
+        H.d1 = 0.f; H.d2 = 0.f;
       }
     }
     act = res > PGS_RESIDUAL;
   }
+  const float (&v)[3] = H.c.v;
+  const float (&w)[3] = H.c.w;
 #pragma unroll
   for (int i = 0; i < 3; ++i) { cbm.v[i] = v[i]; cbm.w[i] = w[i]; cbm.pos[i] = fmaf(v[i], DT, cb.pos[i]); }
   // quaternion exponential map; half angle = |w| dt / 2 is far inside [-pi/4, pi/4] (|w| < 370 rad/s): polynomials only

@@ -7,10 +7,34 @@ The gradient buckets are 0.27-0.55 MB (TD3 twin critic 137 218 params, actor 68 
 network's gradients live in ONE contiguous buffer (param.grad are views into it) and go out as ONE all-reduce.
 Works with backend "nccl" (NVLink/NVSwitch) and "gloo" (CPU tests).
 """
+import gc
 import os
+import weakref
 
 import torch
 import torch.distributed as dist
+
+# objects holding CUDA graphs that captured NCCL collectives (VectorTrainer registers itself): shutdown() makes them drop
+# those graphs first -- ncclCommDestroy blocks for ever while an instantiated graph still references the communicator
+# (measured on 2 x B200, torch 2.11 / NCCL 2.28: the run finished, then hung in destroy_process_group)
+_GRAPH_HOLDERS = weakref.WeakSet()
+
+
+def register_graph_holder(obj):
+    """obj.release_graphs() will be called by shutdown() before the process group is destroyed"""
+    _GRAPH_HOLDERS.add(obj)
+
+
+def shutdown():
+    """ordered teardown of a multi-process run: drop recorded collectives, drain the device, barrier, destroy the group"""
+    for h in list(_GRAPH_HOLDERS):
+        h.release_graphs()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def init_from_env(backend=None):

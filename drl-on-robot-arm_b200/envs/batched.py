@@ -217,6 +217,35 @@ class BatchedArmEnv(ArmSimHandle):
         L.check(L.lib().armsim_explore(self.h, actor_out.data_ptr(), float(noise_std), float(clip), out.data_ptr(), self._stream()))
         return out
 
+    def policy_act(self, policy, obs=None, noise_std=None, clip=0.0, out=None):
+        """The acting policy in ONE launch (armsim_policy_act): out = policy(obs) [+ noise_std * N(0,1), clipped], read
+        straight from the nn.Linear parameters of `policy` (algo.nets.PolicyNet: fc1, fc2, fc3, action_bound; hidden 256,
+        fp32, on this device).  noise_std=None returns the bare policy output.  Replaces policy(obs) + explore()."""
+        t = self.torch
+        obs = self.obs if obs is None else obs
+        if obs.dtype != t.float32 or not obs.is_contiguous():
+            obs = obs.to(t.float32).contiguous()
+        if out is None:
+            out = t.empty((self.n, self.act_dim), device=self.device, dtype=t.float32)
+        ps = [policy.fc1.weight, policy.fc1.bias, policy.fc2.weight, policy.fc2.bias, policy.fc3.weight, policy.fc3.bias]
+        for p_ in ps:
+            if p_.dtype != t.float32 or not p_.is_contiguous() or p_.device != self.device:
+                raise ValueError("policy_act: parameters must be contiguous fp32 tensors on %s" % self.device)
+        L.check(L.lib().armsim_policy_act(self.h, obs.data_ptr(), *[p_.data_ptr() for p_ in ps], int(policy.fc2.weight.shape[0]),
+                                          float(policy.action_bound), -1.0 if noise_std is None else float(noise_std), float(clip),
+                                          out.data_ptr(), self._stream()))
+        return out
+
+    @staticmethod
+    def policy_supported(policy, obs_dim, act_dim):
+        """can armsim_policy_act run this module? (3-layer PolicyNet, hidden 256, obs <= 16, actions <= 4, fp32)"""
+        try:
+            return (policy.fc1.weight.shape == (256, obs_dim) and policy.fc2.weight.shape == (256, 256) and
+                    policy.fc3.weight.shape == (act_dim, 256) and obs_dim <= 16 and act_dim <= 4 and
+                    str(policy.fc1.weight.dtype) == "torch.float32")
+        except AttributeError:
+            return False
+
     def track_episodes(self, reward=None, done=None, success=None):
         """main.py:202-207, :222-229 on the device: running returns + {episodes, successes, return sum} (episode_stats())"""
         r = self.reward if reward is None else reward

@@ -36,7 +36,7 @@ import torch.distributed as dist
 
 from . import _lib as L
 from .config import opt
-from .distributed import allreduce_scalars
+from .distributed import allreduce_scalars, register_graph_holder
 from .metrics import MetricsSink
 
 
@@ -44,7 +44,7 @@ class VectorTrainer:
     def __init__(self, env, agent, replay, noise_std=None, clip_actions=False, batch_size=None, n_train=None,
                  minimal_episodes=None, use_her=True, her_ratio=None, dis_threshold=0.1, window_episodes=None, avg_window=10,
                  sync_every=16, metrics=None, save_prefix=None, use_cuda_graph=True, max_updates_per_sync=None,
-                 fused_bookkeeping=True, graph_updates=None, updates_per_episode=None):
+                 fused_bookkeeping=True, graph_updates=None, updates_per_episode=None, fused_policy=True):
         self.env, self.agent, self.replay = env, agent, replay
         self.device = env.device
         self.n = env.n
@@ -71,6 +71,11 @@ class VectorTrainer:
         self.use_cuda_graph = bool(use_cuda_graph)
         self.max_updates_per_sync = max_updates_per_sync
         self.fused_bookkeeping = bool(fused_bookkeeping)       # armsim_explore / armsim_track_episodes vs torch elementwise ops
+        # single-MLP actors (DDPG, TD3): forward + exploration noise as ONE launch reading the nn.Linear parameters in place
+        # (armsim_policy_act) instead of ~10 PyTorch kernels; double-actor agents keep agent.act()
+        pol = agent.acting_policy() if hasattr(agent, "acting_policy") else None
+        self._policy = pol if (fused_policy and self.fused_bookkeeping and pol is not None and
+                               env.policy_supported(pol, env.obs_dim, env.act_dim)) else None
         # CUDA-graph the learning updates (single GPU; the multi-GPU path keeps eager updates around its all-reduce)
         if graph_updates is None:
             # multi-GPU: the NCCL all-reduce is recorded inside the update graph; train_updates() never leaves a replay in
@@ -79,6 +84,8 @@ class VectorTrainer:
             graph_updates = self.use_cuda_graph and (self.world == 1 or os.environ.get("ARMSIM_GRAPH_NCCL_UPDATES", "1") != "0")
         self.graph_updates = bool(graph_updates)
         self._update_graphs, self._eager_updates = {}, 0
+        if self.world > 1:
+            register_graph_holder(self)
         dev = self.device
         # device-side episode statistics: [episodes finished, successes, sum of finished returns]
         self._stats = torch.zeros(3, device=dev, dtype=torch.float64)
@@ -110,6 +117,12 @@ class VectorTrainer:
 
     def _rollout_body(self):
         env = self.env
+        if self._policy is not None:
+            env.policy_act(self._policy, env.obs, self.noise_std, self.action_bound if self.clip_actions else 0.0, out=self.actions)
+            obs, rew, done, succ = env.step(self.actions, final_obs=True)
+            self.replay.store(self.actions, rew, done, env.final_obs, obs)
+            env.track_episodes(rew, done, succ)
+            return
         a = self.agent.act(env.obs)
         if self.fused_bookkeeping:
             # main.py:200 (+ :117 clip) and :202-207 as two small kernels of the engine instead of ~16 elementwise torch ops
@@ -178,7 +191,7 @@ class VectorTrainer:
                 g = self._update_graphs.get(key)
                 if g is None:
                     if len(self._update_graphs) >= 64:
-                        self._update_graphs.clear()
+                        self.release_graphs()
                     self._stream.synchronize()
                     it0 = self.agent.total_it
                     g = torch.cuda.CUDAGraph()
@@ -195,6 +208,14 @@ class VectorTrainer:
                 # a recorded all-reduce runs on THIS stream, eager collectives on the process group's own one: never leave
                 # a replay in flight where the caller may issue another collective (NCCL needs one order on every rank)
                 self._stream.synchronize()
+
+    def release_graphs(self):
+        """drop the recorded update cycles (they hold NCCL work when world > 1; see distributed.shutdown)"""
+        self._stream.synchronize()
+        for g, _ in self._update_graphs.values():
+            g.reset()
+        self._update_graphs.clear()
+        self._eager_updates = 0
 
     def _one_update(self):
         batch = self.replay.sample(self.batch_size, self.use_her, self.dis_threshold, self.her_ratio)

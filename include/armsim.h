@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ARMSIM_ABI_VERSION 4
+#define ARMSIM_ABI_VERSION 5
 #define ARMSIM_NJ 7            /* arm joints (Kuka iiwa, DianaS1) */
 #define ARMSIM_ACT_DIM 3       /* Cartesian EE servo action, reference envs' action_space */
 #define ARMSIM_TORQUE_DIM 7    /* torque mode action */
@@ -178,6 +178,18 @@ int armsim_host_buffers(ArmSim* sim, float** action, float** obs, float** reward
  *   bookkeeping).  The return sum is kept in 2^-16 fixed point so it does not depend on the order of the atomics.
  * armsim_episode_stats / armsim_set_episode_stats:  {episodes finished, successes, sum of finished returns}; synchronous. */
 int armsim_explore(ArmSim* sim, const float* actor_out_dev, float noise_std, float clip, float* action_out_dev, void* stream);
+
+/* The acting policy of the rollout as ONE launch: action = tanh(fc3(relu(fc2(relu(fc1(obs)))))) * action_bound, then the
+ * exploration step of armsim_explore (same Philox stream, same draw counter) when noise_std >= 0; noise_std < 0 returns
+ * the bare policy output and leaves the draw counters alone.  Replaces `agent.take_action(state)` + noise of
+ * main.py:196-200 for the MLP actors (PolicyNet.forward, algo/TD3/net_mlp.py:29-40; identical in DDPG/DADDPG/DATD3/DARC).
+ * The weights are read where PyTorch keeps them: nn.Linear layout, row-major [out, in], fp32, device pointers:
+ * w1 [hidden, obs_dim], w2 [hidden, hidden], w3 [action_dim, hidden], biases [out].  hidden must be 256 (the reference's
+ * opt.hidden_dim); obs_dim / action_dim are the handle's.  fp32 FFMA throughout (the rollout acts with the policy that is
+ * being trained, to fp32 rounding).  obs_dev f32 [n, obs_dim]; action_out_dev f32 [n, action_dim]. */
+int armsim_policy_act(ArmSim* sim, const float* obs_dev, const float* w1, const float* b1, const float* w2, const float* b2,
+                      const float* w3, const float* b3, int32_t hidden, float action_bound, float noise_std, float clip,
+                      float* action_out_dev, void* stream);
 int armsim_track_episodes(ArmSim* sim, const float* reward_dev, const uint8_t* done_dev, const uint8_t* success_dev,
                           void* stream);
 int armsim_episode_stats(ArmSim* sim, double out[3]);

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for sym in declared:
         assert hasattr(lib, sym), "libarmsim.so does not export %s" % sym
     assert sorted(pkg._lib.EXPORTS) == declared
-    assert lib.armsim_abi_version() == 4
+    assert lib.armsim_abi_version() == pkg._lib.ABI_VERSION == 5
 
 
 def test_library_is_sm100a_only(pkg):

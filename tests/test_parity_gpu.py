@@ -289,14 +289,17 @@ def test_cube_tasks_teacher_forced(pkg, oracle, torch_cuda, task, tid, n, robot)
     starts from the oracle's state (teacher forcing), so each comparison is one fused step = IK + one (push) or two
     (pick) cube sim steps.  Tolerances (fp32 device vs fp64 oracle):
       EE                      5e-6 m   equal IK iteration counts, converged
-                              1e-2 m   envs that ran into Bullet's 20-iteration cap (pick: joint 7 is never teleported,
+                              --       envs that ran into Bullet's 20-iteration cap (pick: joint 7 is never teleported,
                                        rl_pick_env.py:342, so the orientation error cannot vanish; ~0.15 % of the
-                                       env-steps): both sides made the same 20 DLS updates from the same start, but a
-                                       NON-converging damped-least-squares iteration with lambda = 1e-5 amplifies the
-                                       fp32 rounding of its first updates ALONG THE ARM'S NULL SPACE (7 joints, 6 task
-                                       rows: measured up to 0.33 rad in one joint while the EE agrees), so only the
-                                       EE -- what the env observes and the cube feels -- is claimed, to 1 cm, and
-                                       their cubes are compared at 2e-3 m
+                                       env-steps): both sides make the same 20 DLS updates from the same start, but a
+                                       NON-converging damped-least-squares iteration with lambda = 1e-5 is CHAOTIC --
+                                       the fp64 oracle itself moves its EE by up to 7 cm (median 8e-5 m, p90 9e-3 m)
+                                       when the action changes by 2e-6 relative, i.e. by one fp32 rounding.  So the
+                                       claim for these envs is distributional: the device-vs-oracle EE error must
+                                       stay within 5x the oracle's OWN sensitivity to that perturbation (a twin
+                                       oracle stepped with action * (1 + 2e-6)) at the median and the 90th
+                                       percentile, and within the 0.2 m a workspace-clipped target allows at worst;
+                                       their cubes are compared only where the EE agrees to 1e-3 m
       cube position / obs     5e-5 m   (up to 50 Gauss-Seidel sweeps each side; recovery speeds up to ~3 m/s), for all
                                        but 0.5 % of the envs -- the contact set is a discontinuous function of the pose
                                        (a corner entering the 5 mm margin, the capsule touching), so an env that sits
@@ -312,6 +315,9 @@ def test_cube_tasks_teacher_forced(pkg, oracle, torch_cuda, task, tid, n, robot)
     if robot == "diana_s1":
         okw["robot"] = O.ROBOT_DIANA
     ora = O.OracleSim(O.default_config(tid, n_envs=n, seed=8, **okw))
+    twin = O.OracleSim(O.default_config(tid, n_envs=n, seed=8, **okw))     # sensitivity probe for the capped-IK envs
+    twin.reset()
+    cap_err, cap_sens = [], []
     rng = np.random.default_rng(8)
     fields = [O.F_Q, O.F_CUBE_POS, O.F_CUBE_QUAT, O.F_CUBE_LINVEL, O.F_CUBE_ANGVEL, O.F_LAST_DIST, O.F_GRIP]
     # bring half of the arms down onto their cubes so that contacts are exercised
@@ -330,8 +336,11 @@ def test_cube_tasks_teacher_forced(pkg, oracle, torch_cuda, task, tid, n, robot)
         a[n // 2:] = rng.uniform(-0.4, 0.4, (n - n // 2, 3)).astype(np.float32)
         a += rng.normal(0, 0.05, a.shape).astype(np.float32)
         v0 = ora.get_state(O.F_CUBE_LINVEL)
+        for f in fields + [O.F_GOAL]:
+            twin.set_state(f, ora.get_state(f))
         og, rg, dg, sg = env.step_host(a)
         oo, ro, do, so = ora.step(a)
+        ot = twin.step((a * np.float32(1.0 + 2e-6)).astype(np.float32))[0]
         it_g, it_o = env.get_state(L.F_IK_ITERS), ora.get_state(O.F_IK_ITERS)
         same = (it_g == it_o) & (it_o < 20)
         cap = (it_g == 20) & (it_o == 20)
@@ -339,7 +348,9 @@ def test_cube_tasks_teacher_forced(pkg, oracle, torch_cuda, task, tid, n, robot)
         assert eerr[same].max() <= 5e-6
         if cap.any():
             n_cap += int(cap.sum())
-            assert eerr[cap].max() <= 1e-2, eerr[cap].max()
+            cap_err += list(eerr[cap]); cap_sens += list(np.abs(ot[:, :3] - oo[:, :3]).max(axis=1)[cap])
+            assert eerr[cap].max() <= 0.2, eerr[cap].max()
+            cap = cap & (eerr <= 1e-3)        # cubes of capped envs: only where the EE (the cube's input) agrees
         gg, go = env.get_state(L.F_GRIP), ora.get_state(O.F_GRIP)
         ok = same | cap
         if task == "pick":
@@ -363,6 +374,9 @@ def test_cube_tasks_teacher_forced(pkg, oracle, torch_cuda, task, tid, n, robot)
         assert np.abs(rg - ro)[moving & (np.abs(np.abs(ro) - 1.0) > 1e-6)].max(initial=0) <= 2e-2   # r = -100 * (distance change)
     assert n_cmp > 0.97 * n * steps and n_bad <= 0.005 * n_cmp, (n_cmp, n_bad)
     assert touched > 0.02 * n * steps, touched            # contacts with the arm were really exercised
+    if len(cap_err) >= 20:                                # capped-IK envs: within 5x the oracle's own sensitivity
+        for pct, floor in ((50, 1e-3), (90, 1e-2)):
+            assert np.percentile(cap_err, pct) <= max(floor, 5.0 * np.percentile(cap_sens, pct)), (pct, np.percentile(cap_err, pct))
     if task == "pick":
         assert (ora.get_state(O.F_GRIP) > 0).any()          # some grippers did close on their cube
     env.close()

@@ -90,6 +90,74 @@ def test_explore_noise_kernel(pkg, torch_cuda):
         e.close()
 
 
+@pytest.mark.parametrize("task,n", [("reach", 4096), ("push", 1000), ("pick", 33)])
+def test_policy_act_matches_the_torch_actor(pkg, torch_cuda, task, n):
+    """armsim_policy_act (PolicyNet.forward of algo/TD3/net_mlp.py:29-40 as one launch, fp32 FFMA): equals the PyTorch
+    module on the same parameters to 5e-6 (summation order only), ragged batch sizes included; with exploration its noise
+    is bit-identical to armsim_explore applied to the bare output (same Philox stream and draw counter); picks up
+    in-place parameter updates (it reads the nn.Linear storage) and replays from a CUDA graph with fresh noise."""
+    torch = torch_cuda
+    from drl_on_robot_arm_b200.algo.nets import PolicyNet
+    torch.manual_seed(11)
+    env = pkg.BatchedArmEnv(task, n_envs=n, device="cuda:0", seed=5)
+    twin = pkg.BatchedArmEnv(task, n_envs=n, device="cuda:0", seed=5)
+    S = env.obs_dim
+    net = PolicyNet(S, 256, 3, 0.7).to("cuda:0")
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(3.0)                                  # spread the pre-activations over tanh's range
+    assert env.policy_supported(net, S, 3)
+    obs = (torch.rand((n, S), device="cuda") - 0.5) * 2.0
+    with torch.no_grad():
+        want = net(obs)
+    got = env.policy_act(net, obs)
+    assert float((got - want).abs().max()) <= 5e-6, float((got - want).abs().max())
+    assert float(want.abs().max()) > 0.5 and float(want.abs().min()) < 0.05      # saturated and linear outputs both present
+    noisy = env.policy_act(net, obs, noise_std=0.4, clip=0.7)
+    assert torch.equal(noisy, twin.explore(got, 0.4, clip=0.7))
+    noisy2 = env.policy_act(net, obs, noise_std=0.4, clip=0.7)
+    assert not torch.equal(noisy, noisy2) and torch.equal(noisy2, twin.explore(got, 0.4, clip=0.7))
+    with torch.no_grad():
+        net.fc3.bias.add_(0.25)
+        want2 = net(obs)
+    assert float((env.policy_act(net, obs) - want2).abs().max()) <= 5e-6
+    out = torch.empty_like(got)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        env.policy_act(net, obs, noise_std=1.0, out=out)
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            env.policy_act(net, obs, noise_std=1.0, out=out)
+        g.replay(); st.synchronize(); r1 = out.clone()
+        g.replay(); st.synchronize(); r2 = out.clone()
+    assert not torch.equal(r1, r2)
+    z = ((r1 - want2) / 1.0).double().cpu().numpy().ravel()
+    if n >= 1000:
+        assert abs(z.mean()) < 0.08 and abs(z.std() - 1.0) < 0.08
+    bad = PolicyNet(S, 128, 3, 0.7).to("cuda:0")
+    assert not env.policy_supported(bad, S, 3)
+    with pytest.raises(Exception):
+        env.policy_act(bad, obs)
+    for e in (env, twin):
+        e.close()
+
+
+def test_fused_policy_rollout_matches_torch_actor_rollout(pkg, torch_cuda):
+    """the trainer's rollout with the one-launch policy == the rollout through agent.act() + explore (noise off: the
+    action differs by fp32 summation order only, so joint angles agree to 1e-4 rad over 40 steps and the episode
+    bookkeeping is identical)"""
+    res = []
+    for fused in (True, False):
+        tr = _mk(pkg, n=256, minimal_episodes=10 ** 9, noise_std=0.0, fused_policy=fused)
+        assert (tr._policy is not None) == fused
+        tr.run(40)
+        res.append((tr.env.get_state(0).copy(), tr.stats.cpu().numpy().copy()))
+        tr.env.close(); tr.replay.close()
+    assert np.abs(res[0][0] - res[1][0]).max() <= 1e-4
+    assert np.array_equal(res[0][1][:2], res[1][1][:2])
+
+
 def test_track_episodes_matches_host_bookkeeping(pkg, torch_cuda):
     """armsim_track_episodes (main.py:202-207, :222-229) against the same bookkeeping done in numpy float64"""
     torch = torch_cuda
@@ -121,7 +189,7 @@ def test_fused_and_torch_bookkeeping_agree(pkg, torch_cuda):
     torch = torch_cuda
     res = []
     for fused in (True, False):
-        tr = _mk(pkg, n=200, minimal_episodes=10 ** 9, noise_std=0.0, fused_bookkeeping=fused)
+        tr = _mk(pkg, n=200, minimal_episodes=10 ** 9, noise_std=0.0, fused_bookkeeping=fused, fused_policy=False)
         tr.env.close()
         from drl_on_robot_arm_b200.distributed import make_sharded_env
         tr.env = make_sharded_env("reach", 200, device="cuda:0", seed=3, auto_reset=True, max_steps=12)

@@ -5,8 +5,13 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import faulthandler
+
 import torch
 import torch.distributed as dist
+
+if os.environ.get("HANG_DUMP_S"):          # diagnosis: print every thread's stack and exit if the check has not finished by then
+    faulthandler.dump_traceback_later(float(os.environ["HANG_DUMP_S"]), exit=True)
 
 import drl_on_robot_arm_b200 as pkg  # noqa: F401
 from drl_on_robot_arm_b200 import distributed as D
@@ -31,6 +36,5 @@ if rank == 0:
     print("updates", out["updates"], "episodes", out["episodes"], "replicas identical:", same, "shards differ:", differ)
     if same and differ and out["updates"] > 0:
         print("DIST_TRAIN_OK")
-dist.barrier()
-dist.destroy_process_group()
+D.shutdown()
 sys.exit(0 if (same and differ) else 1)

@@ -68,5 +68,4 @@ if rank == 0:
     if out:
         json.dump(summary, open(out, "w"), indent=1)
 if world > 1:
-    torch.distributed.barrier()
-    torch.distributed.destroy_process_group()
+    D.shutdown()
