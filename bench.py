@@ -631,20 +631,25 @@ def side_measurements(torch, pkg, dev, peak_gbs):
         from drl_on_robot_arm_b200 import train
         tr = train.make_trainer(task="reach", algo="TD3_MLP", n_envs=N_ENVS, device=dev, seed=0, minimal_episodes=10 ** 12,
                                 sync_every=10 ** 9)
-        for _ in range(20):
+        tr.sync_every = 50                              # chunk graphs of 50 lockstep steps (VectorTrainer.rollout_chunk)
+        for _ in range(50):
             tr.rollout_step()
+        done_steps = 0
+        while done_steps < 200:                         # warm-up incl. the chunk-graph capture
+            done_steps += tr.rollout_chunk(10 ** 9)
         tr._stream.synchronize()
-        k = 1000
+        k = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(tr._stream)
-        for _ in range(k):
-            tr.rollout_step()
+        while k < 2000:
+            k += tr.rollout_chunk(10 ** 9)
         e1.record(tr._stream)
         tr._stream.synchronize()
         sec = e0.elapsed_time(e1) * 1e-3 / k
         out["rollout_with_td3_actor"] = {"env_steps_per_s": N_ENVS / sec, "us_per_rollout_step": sec * 1e6, "n_envs": N_ENVS,
-                                         "what": "CUDA-graph replay of {TD3 actor forward (PyTorch), armsim_explore N(0,0.98) noise, fused reach "
-                                                 "step, trajectory-replay store, armsim_track_episodes} per lockstep step, device-timed"}
+                                         "what": "CUDA-graph replays (50 lockstep steps per graph) of {TD3 actor forward + N(0,0.98) exploration noise as ONE "
+                                                 "launch (armsim_policy_act on the PyTorch parameters), fused reach step, trajectory-replay store, "
+                                                 "armsim_track_episodes}, device-timed"}
         tr.env.close(); tr.replay.close()
     except Exception as e:  # secondary numbers must never kill the headline line
         out.setdefault("other_configs", {})["error"] = repr(e)

@@ -426,8 +426,6 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   // per-step payload is small enough for PCIe latency, not bandwidth, to dominate; DMA copies beyond that
   s->zero_copy = n <= 65536;
   s->grid = (s->n + LANE_BLOCK - 1) / LANE_BLOCK;
-  // tuning experiment: pad small grids with blocks that own no env (they only ring their doorbell)
-  if (const char* mg = getenv("ARMSIM_MIN_GRID")) s->grid = std::max(s->grid, atoi(mg));
   const size_t flag_bytes = pad((size_t)s->grid * sizeof(unsigned int));
   if (cudaMalloc((void**)&s->d_io, s->act_bytes + s->out_bytes) != cudaSuccess ||
       cudaMalloc((void**)&s->d_stats, 3 * sizeof(unsigned long long)) != cudaSuccess ||

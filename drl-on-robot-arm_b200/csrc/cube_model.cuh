@@ -34,7 +34,8 @@ constexpr float TABLE_Z = -0.025f, GROUND_Z = -0.65f;
 constexpr float TABLE_X0 = -0.25f, TABLE_X1 = 1.25f, TABLE_Y0 = -0.5f, TABLE_Y1 = 0.5f;
 constexpr float MARGIN = 0.005f;
 constexpr int PGS_ITERS = 50;                 // pybullet numSolverIterations
-constexpr float PGS_RESIDUAL = 1e-7f;         // pybullet m_leastSquaresResidualThreshold
+constexpr float PGS_RESIDUAL = 1e-7f;         // pybullet m_leastSquaresResidualThreshold (on the squared velocity change)
+constexpr float PGS_RESIDUAL_ROOT = 3.16227766e-4f;
 constexpr float DAMP = 0.99982992284f;
 constexpr int MAX_CORNERS = 4, MAX_PROXIES = 3;
 constexpr float PUSH_R = 0.04f, PUSH_A0 = -0.10f, PUSH_A1 = 0.005f;
@@ -194,28 +195,36 @@ CUBE_FN float gripper_distance(const State& cb, const float (&ee)[3], const floa
 //    B (times 1/k_i: c2, c1) are computed once per sim step.  Left on the chain: one FMA, the clamp, one subtraction
 //    (4 operations per row instead of 10).  Algebraically identical to the oracle's update, rounding differs at 1e-7.
 //
-// Per-thread column of dynamic shared memory: word k of the calling thread is scratch[k * SLOT_STRIDE + threadIdx.x]
-// (conflict-free).  The accumulated impulses and the twist history live in registers.
+// Per-thread column of dynamic shared memory in 16-byte vectors: vector V of the calling thread is the float4 at
+// scratch[(V * SLOT_STRIDE + threadIdx.x) * 4] (a warp reads 512 contiguous bytes: conflict-free LDS.128, a quarter of
+// the load instructions of a word layout -- with one warp per scheduler the sweep is bound by instruction issue).
+//   corner slot c : V = 4c   (r0, r1, r2, h)        V = 4c+1 / +2 / +3 : row n / t1 / t2 = (1/k, c1, c2, k)
+//   capsule p     : V = 16 + 9p + 3j + {0,1,2} for row j = (d0,d1,d2,x0) (x1,x2,1/k,c1) (c2,k,h,-)
+// The accumulated impulses and the twist history live in registers.
 #if defined(__CUDACC__)
 constexpr int SLOT_STRIDE = 128;                 // = LANE_BLOCK (threads per block of every kernel that steps cubes)
 #else
 constexpr int SLOT_STRIDE = 1;
+struct float4 { float x, y, z, w; };
 #endif
-constexpr int CORNER_WORDS = 16;                 // r[3], k n/t1/t2, 1/k n/t1/t2, c1 n/t1/t2, c2 n/t1/t2, h
-constexpr int ROW_WORDS = 10;                    // dir[3], r x dir [3], k, 1/k, c1, c2
-constexpr int PROXY_WORDS = 3 * ROW_WORDS + 1;   // rows n, t1, t2 + h
-template <bool PICK> constexpr int scratch_words() { return MAX_CORNERS * CORNER_WORDS + (PICK ? 3 : 1) * PROXY_WORDS; }
-template <bool PICK> constexpr int scratch_bytes() { return scratch_words<PICK>() * SLOT_STRIDE * 4; }   // push 47.5 KB, pick 78.5 KB
+constexpr int CORNER_VECS = 4, PROXY_VECS = 9;
+template <bool PICK> constexpr int scratch_vecs() { return MAX_CORNERS * CORNER_VECS + (PICK ? 3 : 1) * PROXY_VECS; }
+template <bool PICK> constexpr int scratch_bytes() { return scratch_vecs<PICK>() * SLOT_STRIDE * 16; }   // push 50 KB, pick 86 KB
 
 #if defined(__CUDACC__)
-extern __shared__ float cube_scratch[];
-CUBE_FN float* scratch_column() { return cube_scratch + threadIdx.x; }
+extern __shared__ __align__(16) float cube_scratch[];
+CUBE_FN float* scratch_column() { return cube_scratch + threadIdx.x * 4; }
 CUBE_FN bool warp_any(bool p) { return __any_sync(__activemask(), p) != 0; }
 #else
-static float cube_scratch_host[MAX_CORNERS * CORNER_WORDS + 3 * PROXY_WORDS];
+static float cube_scratch_host[(MAX_CORNERS * CORNER_VECS + 3 * PROXY_VECS) * 4];
 CUBE_FN float* scratch_column() { return cube_scratch_host; }
 CUBE_FN bool warp_any(bool p) { return p; }
 #endif
+CUBE_FN float4 ldv(const float* sm, int V) { return *reinterpret_cast<const float4*>(sm + V * (SLOT_STRIDE * 4)); }
+CUBE_FN void stv(float* sm, int V, float a, float b, float c, float d) {
+  float4 t; t.x = a; t.y = b; t.z = c; t.w = d;
+  *reinterpret_cast<float4*>(sm + V * (SLOT_STRIDE * 4)) = t;
+}
 
 struct Twist { float v[3], w[3]; };
 // a = twist after row i-3, b = after row i-2, c = after row i-1; d1 = impulse change of row i-1, d2 = of row i-2
@@ -241,14 +250,19 @@ CUBE_FN float row_impulse(float jv, float ik, float c1, float c2, float lamh, co
   return fmaf(-c1, H.d1, g);
 }
 
-// The three rows of corner slot c.  The plane normal is +z, for which btPlaneSpace1 (tangents()) gives t1 = (0,-1,0),
-// t2 = (1,0,0): J_n = (0,0,1, r1,-r0,0), J_t1 = (0,-1,0, r2,0,-r0), J_t2 = (1,0,0, 0,r2,-r1).
-CUBE_FN void corner_rows(const float* c, float (&lam)[3], History& H, float& res) {
-  constexpr int S = SLOT_STRIDE;
-  const float r0 = c[0], r1 = c[1 * S], r2 = c[2 * S];
+// Largest |velocity change along a row| of the sweep; pybullet's test "squared residual <= 1e-7" becomes
+// |dv| <= sqrt(1e-7) at the end of the sweep (one multiply + one max per row).
+CUBE_FN void track_residual(float dl, float k, float& res) { res = fmaxf(res, fabsf(dl * k)); }
+
+// The three rows of corner slot c (vectors V .. V+3).  The plane normal is +z, for which btPlaneSpace1 (tangents())
+// gives t1 = (0,-1,0), t2 = (1,0,0): J_n = (0,0,1, r1,-r0,0), J_t1 = (0,-1,0, r2,0,-r0), J_t2 = (1,0,0, 0,r2,-r1).
+CUBE_FN void corner_rows(const float* sm, int V, float (&lam)[3], History& H, float& res) {
+  const float4 g = ldv(sm, V);
+  const float r0 = g.x, r1 = g.y, r2 = g.z;
   {  // normal
+    const float4 q = ldv(sm, V + 1);                 // 1/k, c1, c2, k
     const float jv = fmaf(r1, H.a.w[0], fmaf(-r0, H.a.w[1], H.a.v[2]));
-    const float nl = fmaxf(row_impulse(jv, c[6 * S], c[9 * S], c[12 * S], lam[0] + c[15 * S], H), 0.0f);
+    const float nl = fmaxf(row_impulse(jv, q.x, q.y, q.z, lam[0] + g.w, H), 0.0f);
     const float dl = nl - lam[0];
     lam[0] = nl;
     const float dli = dl * INV_INERTIA;
@@ -256,14 +270,14 @@ CUBE_FN void corner_rows(const float* c, float (&lam)[3], History& H, float& res
     un.v[2] += dl;
     un.w[0] = fmaf(dli, r1, un.w[0]);
     un.w[1] = fmaf(-dli, r0, un.w[1]);
-    const float dv = dl * c[3 * S];
-    res = fmaxf(res, dv * dv);
+    track_residual(dl, q.w, res);
     advance(H, un, dl);
   }
   const float lim = MU * lam[0];
   {  // t1
+    const float4 q = ldv(sm, V + 2);
     const float jv = fmaf(r2, H.a.w[0], fmaf(-r0, H.a.w[2], -H.a.v[1]));
-    const float nl = fminf(fmaxf(row_impulse(jv, c[7 * S], c[10 * S], c[13 * S], lam[1], H), -lim), lim);
+    const float nl = fminf(fmaxf(row_impulse(jv, q.x, q.y, q.z, lam[1], H), -lim), lim);
     const float dl = nl - lam[1];
     lam[1] = nl;
     const float dli = dl * INV_INERTIA;
@@ -271,13 +285,13 @@ CUBE_FN void corner_rows(const float* c, float (&lam)[3], History& H, float& res
     un.v[1] -= dl;
     un.w[0] = fmaf(dli, r2, un.w[0]);
     un.w[2] = fmaf(-dli, r0, un.w[2]);
-    const float dv = dl * c[4 * S];
-    res = fmaxf(res, dv * dv);
+    track_residual(dl, q.w, res);
     advance(H, un, dl);
   }
   {  // t2
+    const float4 q = ldv(sm, V + 3);
     const float jv = fmaf(r2, H.a.w[1], fmaf(-r1, H.a.w[2], H.a.v[0]));
-    const float nl = fminf(fmaxf(row_impulse(jv, c[8 * S], c[11 * S], c[14 * S], lam[2], H), -lim), lim);
+    const float nl = fminf(fmaxf(row_impulse(jv, q.x, q.y, q.z, lam[2], H), -lim), lim);
     const float dl = nl - lam[2];
     lam[2] = nl;
     const float dli = dl * INV_INERTIA;
@@ -285,26 +299,26 @@ CUBE_FN void corner_rows(const float* c, float (&lam)[3], History& H, float& res
     un.v[0] += dl;
     un.w[1] = fmaf(dli, r2, un.w[1]);
     un.w[2] = fmaf(-dli, r1, un.w[2]);
-    const float dv = dl * c[5 * S];
-    res = fmaxf(res, dv * dv);
+    track_residual(dl, q.w, res);
     advance(H, un, dl);
   }
 }
 
-// One row of a capsule contact from its slot q (dir, r x dir, k, 1/k, c1, c2)
-CUBE_FN void capsule_row(const float* q, float& lam, float lamh, float lo, float hi, History& H, float& res) {
-  constexpr int S = SLOT_STRIDE;
-  const float d0 = q[0], d1 = q[1 * S], d2 = q[2 * S], x0 = q[3 * S], x1 = q[4 * S], x2 = q[5 * S];
+// One row of a capsule contact (vectors V .. V+2); NORMAL rows add their bias term h and clamp at zero only
+template <bool NORMAL>
+CUBE_FN void capsule_row(const float* sm, int V, float& lam, float lim, History& H, float& res) {
+  const float4 p0 = ldv(sm, V), p1 = ldv(sm, V + 1), p2 = ldv(sm, V + 2);
+  const float d0 = p0.x, d1 = p0.y, d2 = p0.z, x0 = p0.w, x1 = p1.x, x2 = p1.y;
   const float jv = fmaf(d0, H.a.v[0], fmaf(d1, H.a.v[1], d2 * H.a.v[2])) + fmaf(x0, H.a.w[0], fmaf(x1, H.a.w[1], x2 * H.a.w[2]));
-  const float nl = fminf(fmaxf(row_impulse(jv, q[7 * S], q[8 * S], q[9 * S], lamh, H), lo), hi);
+  float nl = row_impulse(jv, p1.z, p1.w, p2.x, NORMAL ? lam + p2.z : lam, H);
+  nl = NORMAL ? fmaxf(nl, 0.0f) : fminf(fmaxf(nl, -lim), lim);
   const float dl = nl - lam;
   lam = nl;
   const float dli = dl * INV_INERTIA;
   Twist un = H.c;
   un.v[0] = fmaf(dl, d0, un.v[0]); un.v[1] = fmaf(dl, d1, un.v[1]); un.v[2] = fmaf(dl, d2, un.v[2]);      // INV_MASS = 1
   un.w[0] = fmaf(dli, x0, un.w[0]); un.w[1] = fmaf(dli, x1, un.w[1]); un.w[2] = fmaf(dli, x2, un.w[2]);
-  const float dv = dl * q[6 * S];
-  res = fmaxf(res, dv * dv);
+  track_residual(dl, p2.y, res);
   advance(H, un, dl);
 }
 
@@ -319,7 +333,6 @@ CUBE_FN void corner_J(const float (&r)[3], float (&jn)[6], float (&j1)[6], float
 // dynamic shared memory in the calling kernel.
 template <bool PICK>
 CUBE_STEP_FN void step(State& cbm, const float (&ee)[3], const float (&Ree)[9], float grip) {
-  constexpr int S = SLOT_STRIDE;
   constexpr int NP = PICK ? 3 : 1;
   State cb = cbm;                    // work on a register copy (the caller's object lives behind a reference)
   History H;
@@ -348,21 +361,18 @@ CUBE_STEP_FN void step(State& cbm, const float (&ee)[3], const float (&Ree)[9], 
         r[i] = ((c & 1) ? Hh[3 * i] : -Hh[3 * i]) + ((c & 2) ? Hh[3 * i + 1] : -Hh[3 * i + 1]) + ((c & 4) ? Hh[3 * i + 2] : -Hh[3 * i + 2]);
       const float gap = cb.pos[2] + r[2] - plane_z;
       if (gap < MARGIN && nc < MAX_CORNERS) {
-        float* s = sm + nc * (CORNER_WORDS * S);
+        stv(sm, nc * CORNER_VECS, r[0], r[1], r[2], gap < 0.f ? -ERP * gap * INV_DT : -gap * INV_DT);   // bias; becomes h = bias / k below
         ++nc;
-        s[0] = r[0]; s[1 * S] = r[1]; s[2 * S] = r[2];
-        s[15 * S] = gap < 0.f ? -ERP * gap * INV_DT : -gap * INV_DT;      // the bias; becomes h = bias / k below
       }
     }
   }
   float rc[MAX_CORNERS][3], bias[MAX_CORNERS];
 #pragma unroll
   for (int c = 0; c < MAX_CORNERS; ++c) {
-    const float* s = sm + c * (CORNER_WORDS * S);
     const bool present = c < nc;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) rc[c][i] = present ? s[i * S] : 0.f;
-    bias[c] = present ? s[15 * S] : 0.f;
+    const float4 g = ldv(sm, c * CORNER_VECS);
+    rc[c][0] = present ? g.x : 0.f; rc[c][1] = present ? g.y : 0.f; rc[c][2] = present ? g.z : 0.f;
+    bias[c] = present ? g.w : 0.f;
   }
   // ---- arm capsules: rows into their slots; prev1 / prev2 = explicit t1 / t2 rows of the block before (GS order)
   float prev1[6], prev2[6], scratch_n[6];
@@ -390,15 +400,14 @@ CUBE_STEP_FN void step(State& cbm, const float (&ee)[3], const float (&Ree)[9], 
     }
     const float c1[3] = {ik[0] * delassus(J[0], prev2), ik[1] * delassus(J[1], J[0]), ik[2] * delassus(J[2], J[1])};
     const float c2[3] = {ik[0] * delassus(J[0], prev1), ik[1] * delassus(J[1], prev2), ik[2] * delassus(J[2], J[0])};
-    float* s = sm + (MAX_CORNERS * CORNER_WORDS + p * PROXY_WORDS) * S;
+    const float hcap = on ? ik[0] * (-ERP * d * INV_DT) : 0.f;                // h = target / k of the normal row
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      float* q = s + k * (ROW_WORDS * S);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) q[i * S] = J[k][i];
-      q[6 * S] = kk[k]; q[7 * S] = ik[k]; q[8 * S] = c1[k]; q[9 * S] = c2[k];
+      const int V = MAX_CORNERS * CORNER_VECS + p * PROXY_VECS + 3 * k;
+      stv(sm, V, J[k][0], J[k][1], J[k][2], J[k][3]);
+      stv(sm, V + 1, J[k][4], J[k][5], ik[k], c1[k]);
+      stv(sm, V + 2, c2[k], kk[k], k == 0 ? hcap : 0.f, 0.f);
     }
-    s[3 * ROW_WORDS * S] = on ? ik[0] * (-ERP * d * INV_DT) : 0.f;          // h = target / k of the normal row
 #pragma unroll
     for (int i = 0; i < 6; ++i) { prev1[i] = J[1][i]; prev2[i] = J[2][i]; }
   }
@@ -419,17 +428,12 @@ CUBE_STEP_FN void step(State& cbm, const float (&ee)[3], const float (&Ree)[9], 
       const float p1 = rc[c - 1][1], p2 = rc[c - 1][2];
       bn2 = -INV_INERTIA * r0 * p2; bn1 = INV_INERTIA * r1 * p2; b12 = INV_INERTIA * r0 * p1;
     }
-    float* s = sm + c * (CORNER_WORDS * S);
-    s[3 * S] = present ? kn : 0.f; s[4 * S] = present ? k1 : 0.f; s[5 * S] = present ? k2 : 0.f;
-    s[6 * S] = ikn; s[7 * S] = ik1; s[8 * S] = ik2;
-    s[9 * S] = ikn * bn2;                           // c1: coupling with the row before
-    s[10 * S] = ik1 * (INV_INERTIA * r1 * r2);      //     B(t1, n)
-    s[11 * S] = ik2 * (INV_INERTIA * r0 * r1);      //     B(t2, t1)
-    s[12 * S] = ikn * bn1;                          // c2: coupling with the row two before
-    s[13 * S] = ik1 * b12;
-    s[14 * S] = ik2 * (-INV_INERTIA * r0 * r2);     //     B(t2, n)
-    s[15 * S] = ikn * bias[c];
-    if (!present) { s[0] = 0.f; s[1 * S] = 0.f; s[2 * S] = 0.f; }
+    const int V = c * CORNER_VECS;
+    stv(sm, V, present ? r0 : 0.f, present ? r1 : 0.f, present ? r2 : 0.f, ikn * bias[c]);
+    //              1/k   c1: coupling with the row before   c2: with the row two before        k
+    stv(sm, V + 1, ikn, ikn * bn2,                           ikn * bn1,                         present ? kn : 0.f);
+    stv(sm, V + 2, ik1, ik1 * (INV_INERTIA * r1 * r2),       ik1 * b12,                         present ? k1 : 0.f);   // B(t1, n)
+    stv(sm, V + 3, ik2, ik2 * (INV_INERTIA * r0 * r1),       ik2 * (-INV_INERTIA * r0 * r2),    present ? k2 : 0.f);   // B(t2, t1), B(t2, n)
   }
 
   // ---- sweeps: every lane stops at ITS OWN convergence (pybullet's residual test) or after 50; a warp runs as long
@@ -447,21 +451,21 @@ CUBE_STEP_FN void step(State& cbm, const float (&ee)[3], const float (&Ree)[9], 
   for (int it = 0; act && it < PGS_ITERS; ++it) {
     float res = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAX_CORNERS; ++c) corner_rows(sm + c * (CORNER_WORDS * S), lam[c], H, res);
+    for (int c = 0; c < MAX_CORNERS; ++c) corner_rows(sm, c * CORNER_VECS, lam[c], H, res);
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       if (any_cap[p]) {
-        const float* s = sm + (MAX_CORNERS * CORNER_WORDS + p * PROXY_WORDS) * S;
-        capsule_row(s, lamc[p][0], lamc[p][0] + s[3 * ROW_WORDS * S], 0.0f, 1e30f, H, res);
+        const int V = MAX_CORNERS * CORNER_VECS + p * PROXY_VECS;
+        capsule_row<true>(sm, V, lamc[p][0], 0.f, H, res);
         const float lim = MU * lamc[p][0];
-        capsule_row(s + ROW_WORDS * S, lamc[p][1], lamc[p][1], -lim, lim, H, res);
-        capsule_row(s + 2 * ROW_WORDS * S, lamc[p][2], lamc[p][2], -lim, lim, H, res);
+        capsule_row<false>(sm, V + 3, lamc[p][1], lim, H, res);
+        capsule_row<false>(sm, V + 6, lamc[p][2], lim, H, res);
       } else {                        // three rows that change nothing: the history collapses onto the current twist
         H.a = H.c; H.b = H.c;
         H.d1 = 0.f; H.d2 = 0.f;
       }
     }
-    act = res > PGS_RESIDUAL;
+    act = res > PGS_RESIDUAL_ROOT;
   }
   const float (&v)[3] = H.c.v;
   const float (&w)[3] = H.c.w;

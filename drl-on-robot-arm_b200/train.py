@@ -93,6 +93,7 @@ class VectorTrainer:
         self.actions = torch.zeros((self.n, env.act_dim), device=dev)
         self.obs = None
         self._graph = None
+        self._chunk_graph, self._chunk_len = None, 0           # `chunk` consecutive rollout steps as ONE graph launch
         self._stream = torch.cuda.Stream(device=dev)
         # host-side bookkeeping
         self.steps = 0
@@ -170,6 +171,28 @@ class VectorTrainer:
             else:
                 self._graph.replay()
         self.steps += 1
+
+    def rollout_chunk(self, max_steps):
+        """as many lockstep steps as fit before the next statistics read-back (at most `max_steps`), issued as ONE graph
+        launch when a whole chunk of min(sync_every, 64) steps fits: the host then pays one cudaGraphLaunch per chunk
+        instead of one per step (a 4096-env reach step is ~20 us of GPU work, about what a Python-issued launch costs).
+        Same kernels in the same order as rollout_step(), so the results are identical."""
+        chunk = min(self.sync_every, 64)
+        if (not self.use_cuda_graph or self._graph is None or chunk < 2 or max_steps < chunk or
+                self.steps % self.sync_every != 0):
+            self.rollout_step()
+            return 1
+        with torch.cuda.stream(self._stream):
+            if self._chunk_graph is None or self._chunk_len != chunk:
+                self._stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._stream):
+                    for _ in range(chunk):
+                        self._rollout_body()
+                self._chunk_graph, self._chunk_len = g, chunk
+            self._chunk_graph.replay()
+        self.steps += chunk
+        return chunk
 
     # ------------------------------------------------------------------ learning
     def train_updates(self, k):
@@ -272,7 +295,7 @@ class VectorTrainer:
         """advance every env by total_steps lockstep steps, learning as the reference's cadence dictates"""
         end = self.steps + int(total_steps)
         while self.steps < end:
-            self.rollout_step()
+            self.rollout_chunk(end - self.steps)
             if self.steps % self.sync_every == 0 or self.steps >= end:
                 self._sync()
         return {"steps": self.steps, "env_steps": self.steps * self.n * self.world, "updates": self.updates,
