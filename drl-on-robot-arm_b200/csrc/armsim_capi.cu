@@ -510,6 +510,17 @@ int armsim_step_ex(ArmSim* s, const float* action_dev, float* obs_dev, float* re
                      final_obs_dev);
 }
 
+int armsim_step_tracked(ArmSim* s, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                        uint8_t* success_dev, float* final_obs_dev, void* stream) {
+  if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_tracked: null handle");
+  if (!action_dev || !obs_dev || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_step_tracked: null buffer");
+  if (s->cfg.mode == ARMSIM_MODE_TORQUE) return fail(ARMSIM_E_INVALID, "armsim_step_tracked: IK-teleport mode only (use armsim_step_ex + armsim_track_episodes)");
+  DeviceGuard guard(s->cfg.device);
+  HostNotify H{nullptr, nullptr};
+  H.track_stats = s->d_stats;
+  return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream, H, final_obs_dev);
+}
+
 // First half of the host step: stage the actions (unless they already sit in the pinned block) and put the fused
 // launch in flight.  Zero-copy path: one graph launch, nothing else; DMA path (n > 65536): H2D + launch + D2H queued.
 static int host_step_submit(ArmSim* s, const float* action_host) {
@@ -621,10 +632,10 @@ int armsim_policy_act(ArmSim* s, const float* obs_dev, const float* w1, const fl
   const int grid = (s->n + POLICY_ROWS - 1) / POLICY_ROWS;
   if (noise_std >= 0.0f) {
     ensure_smem(policy_mlp_kernel<true>, POLICY_SMEM);
-    policy_mlp_kernel<true><<<grid, POLICY_H, POLICY_SMEM, (cudaStream_t)stream>>>(s->task, s->S, s->n, P, obs_dev, noise_std, clip, action_out_dev);
+    policy_mlp_kernel<true><<<grid, POLICY_THREADS, POLICY_SMEM, (cudaStream_t)stream>>>(s->task, s->S, s->n, P, obs_dev, noise_std, clip, action_out_dev);
   } else {
     ensure_smem(policy_mlp_kernel<false>, POLICY_SMEM);
-    policy_mlp_kernel<false><<<grid, POLICY_H, POLICY_SMEM, (cudaStream_t)stream>>>(s->task, s->S, s->n, P, obs_dev, 0.f, clip, action_out_dev);
+    policy_mlp_kernel<false><<<grid, POLICY_THREADS, POLICY_SMEM, (cudaStream_t)stream>>>(s->task, s->S, s->n, P, obs_dev, 0.f, clip, action_out_dev);
   }
   s->launches += 1;
   CU(cudaGetLastError());

@@ -258,7 +258,37 @@ __device__ __forceinline__ void step_env(const ChainParams& C, const TaskParams&
 struct HostNotify {
   unsigned int* cta_seq;   // device: [gridDim.x] launches seen by each block
   unsigned int* flags;     // mapped host memory: [gridDim.x]
+  unsigned long long* track_stats = nullptr;   // non-null: fold armsim_track_episodes into this launch (armsim_step_tracked)
 };
+
+// main.py:202-207, :222-229 for one warp of envs: accumulate the running return, fold finished episodes into
+// {episodes, successes, return sum}.  Warp-aggregated; the return sum is an integer (2^-16 fixed point) so the total is
+// independent of the order in which warps arrive.  Every lane of the warp must call it (live = false for padding).
+__device__ __forceinline__ void track_warp(const StatePtrs& S, int e, bool live, float reward, bool done, bool success,
+                                           unsigned long long* __restrict__ stats) {
+  bool fin = false, suc = false;
+  long long fx = 0;
+  if (live) {
+    float ret = S.ep_return[e] + reward;
+    fin = done;
+    if (fin) {
+      suc = success;
+      fx = llrintf(ret * 65536.0f);
+      ret = 0.0f;
+    }
+    S.ep_return[e] = ret;
+  }
+  const unsigned mf = __ballot_sync(0xffffffffu, fin);
+  if (mf == 0u) return;
+  const unsigned ms = __ballot_sync(0xffffffffu, suc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fx += __shfl_xor_sync(0xffffffffu, fx, o);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(stats + 0, (unsigned long long)__popc(mf));
+    if (ms) atomicAdd(stats + 1, (unsigned long long)__popc(ms));
+    atomicAdd(stats + 2, (unsigned long long)fx);
+  }
+}
 
 // Programmatic dependent launch (see launch_k in armsim_capi.cu): nothing may be read from global memory before
 // pdl_wait(); pdl_release() lets the next PDL-launched kernel of the stream start its own prologue.
@@ -323,6 +353,7 @@ step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ 
       done[e] = d;
       success[e] = su;
     }
+    if (H.track_stats != nullptr) track_warp(S, e, live, r, d != 0, su != 0, H.track_stats);
 #pragma unroll
     for (int k = 0; k < OD; ++k) st[lane * OD + k] = o[k];
     __syncwarp();
@@ -465,36 +496,13 @@ explore_kernel(const __grid_constant__ TaskParams T, const StatePtrs S, int act_
   }
 }
 
-// main.py:202-207, :222-229 for the whole batch: accumulate the running return, fold finished episodes into
-// {episodes, successes, return sum}.  Warp-aggregated; the return sum is an integer (2^-16 fixed point) so the total is
-// independent of the order in which warps arrive.
+// armsim_track_episodes as its own launch (track_warp above; armsim_step_tracked folds it into the step)
 __global__ void __launch_bounds__(LANE_BLOCK)
 track_episodes_kernel(int n, const StatePtrs S, const float* __restrict__ reward, const uint8_t* __restrict__ done,
                       const uint8_t* __restrict__ success, unsigned long long* __restrict__ stats) {
   const int e = blockIdx.x * LANE_BLOCK + threadIdx.x;
   const bool live = e < n;
-  bool fin = false, suc = false;
-  long long fx = 0;
-  if (live) {
-    float ret = S.ep_return[e] + reward[e];
-    fin = done[e] != 0;
-    if (fin) {
-      suc = success[e] != 0;
-      fx = llrintf(ret * 65536.0f);
-      ret = 0.0f;
-    }
-    S.ep_return[e] = ret;
-  }
-  const unsigned mf = __ballot_sync(0xffffffffu, fin);
-  if (mf == 0u) return;
-  const unsigned ms = __ballot_sync(0xffffffffu, suc);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) fx += __shfl_xor_sync(0xffffffffu, fx, o);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(stats + 0, (unsigned long long)__popc(mf));
-    if (ms) atomicAdd(stats + 1, (unsigned long long)__popc(ms));
-    atomicAdd(stats + 2, (unsigned long long)fx);
-  }
+  track_warp(S, e, live, live ? reward[e] : 0.f, live && done[e] != 0, live && success[e] != 0, stats);
 }
 
 template <int TASK>

@@ -253,17 +253,28 @@ class BatchedArmEnv(ArmSimHandle):
         s = self.success if success is None else success
         L.check(L.lib().armsim_track_episodes(self.h, r.data_ptr(), d.data_ptr(), s.data_ptr(), self._stream()))
 
-    def step(self, action, out=None, final_obs=None):
+    def step(self, action, out=None, final_obs=None, track=False):
         """action: float32 CUDA tensor [N, act_dim].  Returns (obs, reward, done, success) views of the env's own
         output buffers (overwritten by the next step) unless `out` = (obs, reward, done, success) tensors is given.
         final_obs (optional f32 [N, obs_dim] tensor, or True for the env's own buffer `self.final_obs`) receives this
-        step's observation before any in-kernel auto-reset (what a replay buffer stores as next_state)."""
+        step's observation before any in-kernel auto-reset (what a replay buffer stores as next_state).
+        track=True folds track_episodes() of this step into the same launch (armsim_step_tracked; IK-teleport mode)."""
         t = self.torch
         if action.dtype != t.float32 or not action.is_cuda or not action.is_contiguous() or \
                 tuple(action.shape) != (self.n, self.act_dim):
             action = action.to(device=self.device, dtype=t.float32).reshape(self.n, self.act_dim).contiguous()
         obs, rew, done, succ = out if out is not None else (self.obs, self.reward, self.done, self.success)
-        if final_obs is None:
+        if track:
+            fo = None
+            if final_obs is True:
+                if getattr(self, "final_obs", None) is None:
+                    self.final_obs = t.empty_like(self.obs)
+                fo = self.final_obs
+            elif final_obs is not None:
+                fo = final_obs
+            L.check(L.lib().armsim_step_tracked(self.h, action.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                                succ.data_ptr(), fo.data_ptr() if fo is not None else None, self._stream()))
+        elif final_obs is None:
             L.check(L.lib().armsim_step(self.h, action.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
                                         succ.data_ptr(), self._stream()))
         else:

@@ -118,19 +118,23 @@ class VectorTrainer:
 
     def _rollout_body(self):
         env = self.env
+        track = self.fused_bookkeeping and int(env.cfg.mode) == 0    # IK-teleport mode: episode statistics ride in the step launch
         if self._policy is not None:
+            # 3 launches per lockstep step: {actor MLP + exploration noise}, {fused env step + episode statistics}, replay store
             env.policy_act(self._policy, env.obs, self.noise_std, self.action_bound if self.clip_actions else 0.0, out=self.actions)
-            obs, rew, done, succ = env.step(self.actions, final_obs=True)
+            obs, rew, done, succ = env.step(self.actions, final_obs=True, track=track)
             self.replay.store(self.actions, rew, done, env.final_obs, obs)
-            env.track_episodes(rew, done, succ)
+            if not track:
+                env.track_episodes(rew, done, succ)
             return
         a = self.agent.act(env.obs)
         if self.fused_bookkeeping:
-            # main.py:200 (+ :117 clip) and :202-207 as two small kernels of the engine instead of ~16 elementwise torch ops
+            # main.py:200 (+ :117 clip) and :202-207 in the engine's kernels instead of ~16 elementwise torch ops
             env.explore(a, self.noise_std, self.action_bound if self.clip_actions else 0.0, out=self.actions)
-            obs, rew, done, succ = env.step(self.actions, final_obs=True)
+            obs, rew, done, succ = env.step(self.actions, final_obs=True, track=track)
             self.replay.store(self.actions, rew, done, env.final_obs, obs)
-            env.track_episodes(rew, done, succ)
+            if not track:
+                env.track_episodes(rew, done, succ)
             return
         a = a + torch.randn_like(a) * self.noise_std                              # main.py:200
         if self.clip_actions:

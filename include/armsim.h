@@ -144,6 +144,11 @@ int armsim_step(ArmSim* sim, const float* action_dev, float* obs_dev, float* rew
 int armsim_step_ex(ArmSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                    uint8_t* success_dev, float* final_obs_dev, void* stream);
 
+/* armsim_step_ex and armsim_track_episodes (below) of the same step in ONE launch: the rollout's per-step bookkeeping
+ * (main.py:202-207, :222-229) rides in the step kernel's epilogue.  IK-teleport mode only. */
+int armsim_step_tracked(ArmSim* sim, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                        uint8_t* success_dev, float* final_obs_dev, void* stream);
+
 /* Same step through HOST buffers (what a host-side Env.step sees): the actions cross to the device, the fused
  * launch runs, obs/reward/done/success cross back, and the call returns when they are in the caller's buffers.
  * Arbitrary host pointers are staged through the handle's pinned block; see armsim_host_buffers for the copy-free

@@ -158,8 +158,10 @@ def test_fused_policy_rollout_matches_torch_actor_rollout(pkg, torch_cuda):
     assert np.array_equal(res[0][1][:2], res[1][1][:2])
 
 
-def test_track_episodes_matches_host_bookkeeping(pkg, torch_cuda):
-    """armsim_track_episodes (main.py:202-207, :222-229) against the same bookkeeping done in numpy float64"""
+@pytest.mark.parametrize("fused", [False, True])
+def test_track_episodes_matches_host_bookkeeping(pkg, torch_cuda, fused):
+    """armsim_track_episodes (main.py:202-207, :222-229), as its own launch and folded into the step launch
+    (armsim_step_tracked), against the same bookkeeping done in numpy float64"""
     torch = torch_cuda
     n = 1000
     env = pkg.BatchedArmEnv("reach", n_envs=n, device="cuda:0", seed=2, auto_reset=True, max_steps=17, reach_dis=0.05)
@@ -168,8 +170,11 @@ def test_track_episodes_matches_host_bookkeeping(pkg, torch_cuda):
     ret = np.zeros(n); want = np.zeros(3)
     for k in range(120):
         a = (torch.rand((n, 3), device="cuda", generator=gen) * 2 - 1) * 0.7
-        obs, rew, done, succ = env.step(a)
-        env.track_episodes()
+        if fused:
+            obs, rew, done, succ = env.step(a, final_obs=True if k % 2 else None, track=True)
+        else:
+            obs, rew, done, succ = env.step(a)
+            env.track_episodes()
         r, d, s = rew.double().cpu().numpy(), done.cpu().numpy().astype(bool), succ.cpu().numpy().astype(bool)
         ret += r
         want += [d.sum(), (d & s).sum(), ret[d].sum()]

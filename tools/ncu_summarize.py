@@ -42,8 +42,12 @@ def main():
         if h is None or row[0] == "": continue
         try: int(row[0])
         except ValueError: continue
-        n = int(row[si] or 0); files[cur] += n; total += n
-        for i, k in cols: stall[k] += int(row[i] or 0)
+        try:
+            n = int(row[si] or 0); add = [(k, int(row[i] or 0)) for i, k in cols]
+        except (ValueError, IndexError):
+            continue          # a source line whose text (inline asm with quotes / commas) broke the CSV columns
+        files[cur] += n; total += n
+        for k, v in add: stall[k] += v
     st = sum(stall.values()) or 1
     res["warp_stall_sampling"] = {"samples": total,
                                   "stall_share_pct": {k: round(100.0 * v / st, 1) for k, v in stall.most_common() if 100.0 * v / st >= 1.0},
