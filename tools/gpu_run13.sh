@@ -1,0 +1,10 @@
+set -x
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+for algo in DARC_MLP TD3_MLP; do HANG_DUMP_S=80 ALGO=$algo timeout 120 $TR tools/dist_train_check.py > gpurun_out/r02_dist_check_2gpu_$algo.log 2>&1; echo "rc=$?" >> gpurun_out/r02_dist_check_2gpu_$algo.log; grep "updates\|DIST_TRAIN_OK\|^rc=" gpurun_out/r02_dist_check_2gpu_$algo.log; done
+timeout 200 python -m pytest tests/test_train_gpu.py -m gpu -q -k two_gpu > gpurun_out/r02_run13_pytest.log 2>&1; tail -2 gpurun_out/r02_run13_pytest.log
+timeout 300 $TR bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02_bench_2gpu_k20.json 2> gpurun_out/r02_bench_2gpu_k20.err; echo "bench rc=$?"
+python -c "
+import json;d=json.loads(open('gpurun_out/r02_bench_2gpu_k20.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e']['value'],json.dumps(d.get('train_update'))[:1800])"
+tail -3 gpurun_out/r02_bench_2gpu_k20.err
+TRAIN_BUDGET_S=40 timeout 200 $TR tools/train_curve.py reach DARC_MLP 4096 30 gpurun_out/r02_curve_reach_darc_2x4096.json > gpurun_out/r02_curve_darc2.log 2>&1; echo "curve rc=$?"; tail -2 gpurun_out/r02_curve_darc2.log | cut -c1-500
