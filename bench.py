@@ -476,7 +476,7 @@ def run_ours(args):
             "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "rl_%s_env N_envs=%d fused-step kernel, %d x B200 (%d envs total)" % (task, n, world, world * n),
-                       "task": task, "n_envs_per_gpu": n, "robot": "kuka_iiwa", "mode": "ik_teleport", "mapping": "lane",
+                       "task": task, "n_envs_per_gpu": n, "robot": "kuka_iiwa", "mode": "ik_teleport", "mapping": envs[0].mapping,
                        "actions": "U(-0.7,0.7) [%d,N,3] f32 ring on device, launch k uses set k mod %d, the ring is REDRAWN before every "
                                   "timed replay (outside the event pair): a random walk, no env ever repeats an action; auto-reset in kernel" % (N_ACT, N_ACT),
                        "l2": "inputs larger than L2: round-robin over a pool of %d independent %d-env batches "
@@ -493,10 +493,11 @@ def run_ours(args):
                          "traffic": load_traffic(task, n), "traffic_unit": "bytes per launch (dram read + write, ncu --set full, "
                          "profiles/r02_ncu_summary.json; writes still in L2 at kernel end are not counted by ncu)",
                          "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
-                         "kernel": "step_lane_kernel<%s>" % task, "avg_launch_us": launch_us,
+                         "kernel": "step_%s_kernel<%s>" % (envs[0].mapping, task), "avg_launch_us": launch_us,
                          "note": "kernel is fp32-issue / dependent-latency bound, not HBM bound (SURVEY 7): ~6 kFLOP of "
-                                 "dependent fp32 per 118 B; at N=4096 128 warps on 592 SM sub-partitions wait for the "
-                                 "slowest arm's IK (3 DLS iterations typical); see other_configs for the multi-wave sizes"},
+                                 "dependent fp32 per 118 B; at N=4096 every warp sits alone on an SM sub-partition (one FP32 "
+                                 "instruction per ~2 cycles, tools/micro/ffma_rate.cu) and the launch waits for the slowest "
+                                 "arm's IK (3 DLS iterations typical); see other_configs for the multi-wave sizes"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "incl_host_action_write": world * n * e2e_steps / float(np.median(e2e_incl)),
                     "timed": "time inside the public call + the host read of its result, summed over the K steps of a repeat (median of "

@@ -13,7 +13,7 @@ ABI_VERSION = 5
 TASK_REACH, TASK_PUSH, TASK_PICK, TASK_KUKA_REACH = 0, 1, 2, 3
 ROBOT_KUKA_IIWA, ROBOT_DIANA_S1, ROBOT_CUSTOM = 0, 1, 2
 MODE_IK_TELEPORT, MODE_TORQUE = 0, 1
-MAP_AUTO, MAP_LANE, MAP_WARP = 0, 1, 2
+MAP_AUTO, MAP_LANE = 0, 1
 (F_Q, F_QD, F_GOAL, F_STEP, F_EPISODE, F_CUBE_POS, F_CUBE_QUAT, F_CUBE_LINVEL, F_CUBE_ANGVEL, F_LAST_DIST, F_GRIP,
  F_IK_ITERS, F_EP_RETURN, F_EXPLORE_COUNT) = range(14)
 STATE_FIELDS = tuple(f for f in range(14) if f != F_IK_ITERS)      # everything a checkpoint has to carry

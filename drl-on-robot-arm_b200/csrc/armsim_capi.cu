@@ -344,6 +344,7 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   if (cfg->task < 0 || cfg->task > ARMSIM_TASK_KUKA_REACH) return fail(ARMSIM_E_INVALID, "armsim_create: bad task %d", cfg->task);
   if (cfg->mode != ARMSIM_MODE_IK_TELEPORT && cfg->mode != ARMSIM_MODE_TORQUE) return fail(ARMSIM_E_INVALID, "armsim_create: bad mode %d", cfg->mode);
   if (cfg->mode == ARMSIM_MODE_TORQUE && !(cfg->sim_dt > 0.0)) return fail(ARMSIM_E_INVALID, "armsim_create: torque mode needs sim_dt > 0");
+  if (cfg->mapping != ARMSIM_MAP_AUTO && cfg->mapping != ARMSIM_MAP_LANE) return fail(ARMSIM_E_INVALID, "armsim_create: bad mapping %d (one lane per arm is the only mapping)", cfg->mapping);
   if (cfg->ik_max_iters < 0 || cfg->max_steps < 0) return fail(ARMSIM_E_INVALID, "armsim_create: negative iteration / step limit");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);

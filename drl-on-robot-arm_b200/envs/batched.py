@@ -46,6 +46,11 @@ class ArmSimHandle:
         self.act_dim = L.lib().armsim_action_dim(h)
         self.task = task_id
 
+    @property
+    def mapping(self):
+        """resolved thread mapping of the step kernel ("lane": one CUDA lane per arm; see include/armsim.h)"""
+        return {L.MAP_LANE: "lane"}[L.lib().armsim_mapping(self.h)]
+
     def close(self):
         if getattr(self, "h", None):
             self._hb = None              # the views die with the pinned block

@@ -52,10 +52,16 @@ enum {
                                   dynamics -> semi-implicit Euler (sim_dt) -> velocity clip -> joint-limit clamp -> the
                                   task's reward.  obs = task obs followed by q[7], qd[7] (obs_dim + 14)              */
 };
+/* Thread mapping of the step kernels.  There is ONE: a CUDA lane per arm (struct-of-arrays state, warp-local
+ * staging of the row-major I/O).  A four-lanes-per-arm mapping for single-wave batches (the joints' sincos split over
+ * a quad, everything else redundant) was built, proven bit-identical and measured in round 2: 13 % fewer instructions
+ * per warp but 4.08 us against 3.55 us per 4096-arm launch (shuffle latency on the dependent chain, four times the
+ * instruction-fetch and load traffic) -- profiles/r02_quad_mapping_experiment.patch, r02_ncu_summary.json keys
+ * r02_reach_n4096 / r02_reach_n4096_quad.  The `mapping` field of ArmsimConfig is kept for ABI stability and must be
+ * ARMSIM_MAP_AUTO or ARMSIM_MAP_LANE. */
 enum {
-  ARMSIM_MAP_AUTO = 0,         /* pick by n_envs */
-  ARMSIM_MAP_LANE = 1,         /* one CUDA lane per arm (throughput mapping, SoA state)        */
-  ARMSIM_MAP_WARP = 2          /* one warp per arm, joints across lanes (latency mapping)      */
+  ARMSIM_MAP_AUTO = 0,         /* = ARMSIM_MAP_LANE */
+  ARMSIM_MAP_LANE = 1          /* one CUDA lane per arm */
 };
 
 /* A custom 7-DoF serial chain (ARMSIM_ROBOT_CUSTOM).  Same content as include/armsim_robot_models.h. */

@@ -71,6 +71,8 @@ def test_bad_arguments_return_error_codes(pkg):
     assert lib.armsim_create(C.byref(cfg), C.byref(h)) == -1 and b"struct_size" in lib.armsim_last_error()
     cfg = L.default_config(0, n_envs=0)
     assert lib.armsim_create(C.byref(cfg), C.byref(h)) == -1
+    cfg = L.default_config(0, mapping=2)      # the four-lanes-per-arm mapping measured in round 2 was removed (armsim.h)
+    assert lib.armsim_create(C.byref(cfg), C.byref(h)) == -1 and b"mapping" in lib.armsim_last_error()
     assert lib.armsim_default_config(9, C.byref(cfg)) == -1
     assert lib.armsim_step(None, None, None, None, None, None, None) == -1
     assert lib.armsim_obs_dim(None) == -1
