@@ -94,6 +94,8 @@ class VectorTrainer:
         self.obs = None
         self._graph = None
         self._chunk_graph, self._chunk_len = None, 0           # `chunk` consecutive rollout steps as ONE graph launch
+        self._side = torch.cuda.Stream(device=dev)             # replay stores of a chunk graph (overlap the next policy launch)
+        self._actions2 = (self.actions, torch.zeros_like(self.actions))
         self._stream = torch.cuda.Stream(device=dev)
         # host-side bookkeeping
         self.steps = 0
@@ -116,26 +118,39 @@ class VectorTrainer:
                 self.env.set_state(L.F_EP_RETURN, np.zeros(self.n, np.float32))
         self._stream.synchronize()
 
-    def _rollout_body(self):
+    def _rollout_body(self, actions=None, side=None, first=True):
+        """one lockstep step.  `side` (chunk graphs only): the replay store of THIS step is issued on that stream so that
+        it overlaps the NEXT step's policy launch (which only reads obs and writes the other action buffer); the caller
+        alternates `actions` between two buffers and joins the side stream at the end of the chunk."""
         env = self.env
+        actions = self.actions if actions is None else actions
+        main = torch.cuda.current_stream(self.device)
         track = self.fused_bookkeeping and int(env.cfg.mode) == 0    # IK-teleport mode: episode statistics ride in the step launch
-        if self._policy is not None:
-            # 3 launches per lockstep step: {actor MLP + exploration noise}, {fused env step + episode statistics}, replay store
-            env.policy_act(self._policy, env.obs, self.noise_std, self.action_bound if self.clip_actions else 0.0, out=self.actions)
-            obs, rew, done, succ = env.step(self.actions, final_obs=True, track=track)
-            self.replay.store(self.actions, rew, done, env.final_obs, obs)
+
+        def store(obs, rew, done):
+            if side is None:
+                self.replay.store(actions, rew, done, env.final_obs, obs)
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.replay.store(actions, rew, done, env.final_obs, obs)
+
+        if self._policy is not None or self.fused_bookkeeping:
+            clip = self.action_bound if self.clip_actions else 0.0
+            if self._policy is not None:
+                # 3 launches per lockstep step: {actor MLP + exploration noise}, {fused env step + episode statistics}, replay store
+                env.policy_act(self._policy, env.obs, self.noise_std, clip, out=actions)
+            else:
+                # main.py:200 (+ :117 clip) and :202-207 in the engine's kernels instead of ~16 elementwise torch ops
+                env.explore(self.agent.act(env.obs), self.noise_std, clip, out=actions)
+            if side is not None and not first:
+                main.wait_stream(side)          # the previous step's store has read the buffers this step overwrites
+            obs, rew, done, succ = env.step(actions, final_obs=True, track=track)
+            store(obs, rew, done)
             if not track:
                 env.track_episodes(rew, done, succ)
             return
         a = self.agent.act(env.obs)
-        if self.fused_bookkeeping:
-            # main.py:200 (+ :117 clip) and :202-207 in the engine's kernels instead of ~16 elementwise torch ops
-            env.explore(a, self.noise_std, self.action_bound if self.clip_actions else 0.0, out=self.actions)
-            obs, rew, done, succ = env.step(self.actions, final_obs=True, track=track)
-            self.replay.store(self.actions, rew, done, env.final_obs, obs)
-            if not track:
-                env.track_episodes(rew, done, succ)
-            return
         a = a + torch.randn_like(a) * self.noise_std                              # main.py:200
         if self.clip_actions:
             a = a.clamp(-self.action_bound, self.action_bound)                    # main.py:117
@@ -190,9 +205,15 @@ class VectorTrainer:
             if self._chunk_graph is None or self._chunk_len != chunk:
                 self._stream.synchronize()
                 g = torch.cuda.CUDAGraph()
+                overlap = self.fused_bookkeeping or self._policy is not None
                 with torch.cuda.graph(g, stream=self._stream):
-                    for _ in range(chunk):
-                        self._rollout_body()
+                    for k in range(chunk):
+                        if overlap:
+                            self._rollout_body(self._actions2[k % 2], self._side, first=(k == 0))
+                        else:
+                            self._rollout_body()
+                    if overlap:
+                        self._stream.wait_stream(self._side)
                 self._chunk_graph, self._chunk_len = g, chunk
             self._chunk_graph.replay()
         self.steps += chunk

@@ -9,7 +9,22 @@
  * Python control flow).  The arithmetic that lives in the third-party dependency pybullet==3.0.6 (ReadMe.md:17;
  * source absent from /root/reference, wheel not installable) -- calculateInverseKinematics and stepSimulation --
  * is restated from Bullet's published algorithm and is PARITY UNPINNED: no reference test or fixture fixes its
- * numerics.
+ * numerics.  Known open points of the restatement, each with its consequence:
+ *   - Jacobian reference point.  chain_jacobian() takes the linear Jacobian at the origin of the EE link FRAME (the
+ *     point whose position error drives the iteration).  Bullet's processCalculateInverseKinematicsCommand obtains its
+ *     body Jacobian from btInverseDynamics, which (as far as can be recalled without the source) refers it to the
+ *     link's INERTIAL frame: 2 cm up the local z axis for link 7.  If so, Bullet's linear rows
+ *     differ by omega x (0.02 m lever): another iterate path and sometimes another iteration count, but the same
+ *     stopping rule on the link-frame position, i.e. the same end point to within the 1e-4 m residual.  Nothing
+ *     downstream of the step (obs, reward, done) sees more than that.
+ *   - Orientation error is formed as 2 atan2(|v|, w) v/|v| instead of 2 acos(w) v/sqrt(1-w^2): the same value for a
+ *     unit quaternion, better conditioned near zero.
+ *   - An iteration that does not converge within 20 updates (targets clipped to an unreachable workspace corner, or
+ *     pick's untouched joint 7) is CHAOTIC with damping 1e-5: changing the action by 2e-6 relative moves this oracle's
+ *     own end point by up to 7 cm (tests/test_parity_gpu.py::test_cube_tasks_teacher_forced measures it).  For those
+ *     env-steps no implementation, Bullet included, is reproducible beyond the statistics.
+ *   - stepSimulation for the free cube: oracle/cube_model.h states the model; pinned only at system level (the
+ *     reference's untouched-cube return and its push learning curve).
  */
 #ifndef ARMSIM_ORACLE_H
 #define ARMSIM_ORACLE_H
