@@ -295,6 +295,28 @@ __device__ __forceinline__ void track_warp(const StatePtrs& S, int e, bool live,
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Before griddepcontrol.wait a kernel may not READ anything its predecessor writes -- but it may ask L2 to fetch the
+// lines it is about to need: a prefetch returns no data to the SM, and L2 is the coherence point, so whatever the
+// predecessor still writes lands in the very lines that were fetched.  Each warp prefetches the 128-byte lines of its
+// own 32 envs (q[7], goal[3], step, 3 action lines; cube tasks: cube[13], last_dist, grip) while the previous launch
+// of the stream is still running; when the state is HBM-cold (a caller cycling through more env batches than L2
+// holds: bench.py's pool, multi-wave N) the round trip is over by the time the loads issue.  L2-hot state: no-op.
+template <int TASK>
+__device__ __forceinline__ void prefetch_env_lines(const TaskParams& T, const StatePtrs& S, const float* action, int wbase, int lane) {
+  const int n = T.n;
+  const void* p = nullptr;
+  if (lane < 7) p = S.q + (size_t)lane * n + wbase;
+  else if (lane < 10) p = S.goal + (size_t)(lane - 7) * n + wbase;
+  else if (lane == 10) p = S.step + wbase;
+  else if (lane < 14) { if (action != nullptr && (wbase * 3 + (lane - 11) * 32) < n * 3) p = action + (size_t)wbase * 3 + (lane - 11) * 32; }
+  else if (TaskTraits<TASK>::HAS_CUBE) {
+    if (lane < 27) p = S.cube + (size_t)(lane - 14) * n + wbase;
+    else if (lane == 27) p = S.last_dist + wbase;
+    else if (lane == 28) p = S.grip + wbase;
+  }
+  if (p != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ void notify_host(const HostNotify& H) {
   if (H.flags == nullptr) return;
   __syncthreads();
@@ -322,6 +344,7 @@ step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ 
   __shared__ float s_io[LANE_BLOCK / 32][STAGE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wbase = blockIdx.x * LANE_BLOCK + warp * 32;
+  if (wbase < T.n) prefetch_env_lines<TASK>(T, S, H.flags == nullptr ? action : nullptr, wbase, lane);   // (host path: actions sit in mapped host memory)
   pdl_wait();
   pdl_release();
   if (wbase < T.n) {
