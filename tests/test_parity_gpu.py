@@ -624,6 +624,69 @@ def test_full_size_equals_its_shards(pkg, torch_cuda, task, n_total, shard):
         p.close()
 
 
+@pytest.mark.parametrize("task,ee_z", [("push", 0.02), ("pick", 0.255)])
+def test_squeezed_cubes_multi_wave_equals_single_wave(pkg, oracle, torch_cuda, task, ee_z):
+    """The contact solve under load in both builds of the push / pick kernels: with the arm parked low over the cubes -- a
+    third of them squeezed between a capsule and the table, i.e. running all 50 Gauss-Seidel sweeps (the oracle needs
+    15-29 sweeps per sim step on this scene against ~7 for resting cubes) -- one 65536-env handle (register-capped
+    multi-wave build) must equal its 4096-env shards (single-wave build) bit for bit over 6 free-running steps.
+    (Also the harness under which a block-wide straggler hand-off was proven bit-identical before it was measured and
+    dropped: profiles/r02_straggler_handoff_experiment.patch)"""
+    torch = torch_cuda
+    L, O = pkg._lib, oracle
+    n_total, shard = 65536, 4096
+    tid = O.TASK_PUSH if task == "push" else O.TASK_PICK
+    cfg = O.default_config(tid, n_envs=1)
+    q0 = np.array([cfg.init_q[i] for i in range(7)])
+    tq = O.quat_from_euler([cfg.target_rpy[i] for i in range(3)])
+    q_low = q0
+    for z in np.linspace(0.45, ee_z, 12):                      # walk the oracle's IK down to the parking height
+        q_low = O.ik(q_low, [0.5, 0.0, z], tq)[0]
+    ee = O.fk(q_low)[0]
+    assert abs(ee[2] - ee_z) < 2e-3
+    rng = np.random.default_rng(12)
+    cube = np.empty((n_total, 3), np.float32)
+    cube[:, 0] = ee[0] + rng.uniform(-0.08, 0.08, n_total)
+    cube[:, 1] = ee[1] + rng.uniform(-0.08, 0.08, n_total)
+    cube[:, 2] = -0.005
+    cube[::4096 // 8, :2] = ee[:2]                             # ... and in a few blocks nearly every cube right under the arm
+    for b in range(0, n_total, 16384):
+        cube[b:b + 128, 0] = ee[0] + rng.uniform(-0.015, 0.015, 128)
+        cube[b:b + 128, 1] = ee[1] + rng.uniform(-0.015, 0.015, 128)
+    qs = np.tile(q_low.astype(np.float32), (n_total, 1))
+    whole = pkg.BatchedArmEnv(task, n_envs=n_total, seed=6, auto_reset=True, device="cuda:0")
+    parts = [pkg.BatchedArmEnv(task, n_envs=shard, seed=6, auto_reset=True, device="cuda:0", env_id_offset=o)
+             for o in range(0, n_total, shard)]
+    whole.reset()
+    whole.set_state(L.F_Q, qs); whole.set_state(L.F_CUBE_POS, cube)
+    for i, p_ in enumerate(parts):
+        p_.reset()
+        p_.set_state(L.F_Q, qs[i * shard:(i + 1) * shard]); p_.set_state(L.F_CUBE_POS, cube[i * shard:(i + 1) * shard])
+    # the oracle on the first 1024 envs: how many sweeps does this scene take?  (resting cubes: ~7)
+    ora = O.OracleSim(O.default_config(tid, n_envs=1024, seed=6))
+    ora.reset()
+    ora.set_state(O.F_Q, qs[:1024]); ora.set_state(O.F_CUBE_POS, cube[:1024])
+    g = torch.Generator(device="cuda").manual_seed(12)
+    O.pgs_stats(True)
+    moved = 0.0
+    for k in range(6):
+        a = (torch.rand((n_total, 3), device="cuda", generator=g) * 2 - 1) * 0.1
+        o, r, d, s_ = whole.step(a)
+        po, pr, pd, ps = zip(*[tuple(t.clone() for t in p_.step(a[i * shard:(i + 1) * shard].contiguous())) for i, p_ in enumerate(parts)])
+        assert torch.equal(o, torch.cat(po)) and torch.equal(r, torch.cat(pr)), k
+        assert torch.equal(d, torch.cat(pd)) and torch.equal(s_, torch.cat(ps)), k
+        ora.step(a[:1024].cpu().numpy())
+        moved = max(moved, float(np.abs(whole.get_state(L.F_CUBE_LINVEL)).max()))
+    for f in (L.F_CUBE_POS, L.F_CUBE_QUAT, L.F_CUBE_LINVEL, L.F_CUBE_ANGVEL, L.F_GRIP):
+        assert np.array_equal(whole.get_state(f), np.concatenate([p_.get_state(f) for p_ in parts])), f
+    sweeps, steps = O.pgs_stats(True)
+    assert sweeps / steps > 12.0, (sweeps, steps)              # far above the ~7 sweeps of resting cubes: stragglers everywhere
+    assert moved > 0.1
+    whole.close(); ora.close()
+    for p_ in parts:
+        p_.close()
+
+
 @pytest.mark.parametrize("name,odim,dtype", [("RLReachEnv", 6, np.float32), ("RLPushEnv", 9, np.float64),
                                               ("RLPickEnv", 9, np.float64), ("KukaReachEnv", 3, np.float32)])
 def test_drop_in_env_classes(pkg, torch_cuda, name, odim, dtype):
