@@ -279,9 +279,11 @@ static int launch_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, cuda
 #define ARMSIM_STEP_CASE(TASK, ROBOT)                                                                           \
   case (TASK) * 4 + (ROBOT):                                                                                    \
     if (grid > (TaskTraits<TASK>::HAS_CUBE ? DENSE_GRID_THRESHOLD_CUBE : DENSE_GRID_THRESHOLD))                       \
-      lerr = launch_k(step_lane_kernel<TASK, ROBOT, true>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+      lerr = launch_k(step_lane_kernel<TASK, ROBOT, BUILD_DENSE>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+    else if (!TaskTraits<TASK>::HAS_CUBE && grid > PREFETCH_MAX_GRID)                                             \
+      lerr = launch_k(step_lane_kernel<TASK, ROBOT, TaskTraits<TASK>::HAS_CUBE ? BUILD_LATENCY : BUILD_WAVE>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     else                                                                                                          \
-      lerr = launch_k(step_lane_kernel<TASK, ROBOT, false>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
+      lerr = launch_k(step_lane_kernel<TASK, ROBOT, BUILD_LATENCY>, grid, task_smem<TASK>(), st, H.flags == nullptr, s->chain, s->task, s->S, a, o, r, d, su, fo, H); \
     break;
 
 #define ARMSIM_TORQUE_CASE(TASK, ROBOT)                                                                                \

@@ -14,17 +14,25 @@
 #define ARMSIM_LANE_BLOCK 128
 #endif
 constexpr int LANE_BLOCK = ARMSIM_LANE_BLOCK;
-// Two builds of the reach-type step kernels: the default one takes the registers it wants (128, no spills: shortest
-// dependent chain; 4 resident blocks per SM, what a single wave needs) and a "dense" one capped at 80 registers for
-// 6 resident blocks per SM (a few spills, but 50% more warps to hide latency with).  Measured on B200, round 1:
-// dense is +8% env-steps/s at N >= 1M and -7% at N = 4096.  launch_step picks by grid size.
+// Builds of the step kernels, picked by grid size in launch_step (each size gets the build measured fastest there):
+//   BUILD_LATENCY  grids of at most one block per SM (reach N <= 18944): every warp sits alone on a scheduler slot; takes
+//                  the registers it wants (reach 142, push 227, pick 254, no spills: shortest dependent chain) and
+//                  prefetches its env lines before griddepcontrol.wait (prefetch_env_lines below)
+//   BUILD_WAVE     reach-type tasks, up to one full wave of 4 blocks per SM: capped at 128 registers, no prefetch
+//                  (reach N = 32768: 5.1 us; the 142-register build measures 6.0 us there, the 128-register one 3.22
+//                  instead of 3.12 us at N = 4096).  Cube tasks use BUILD_LATENCY up to 2 blocks per SM.
+//   BUILD_DENSE    multi-wave grids: capped at 80 registers (reach: 6 resident blocks per SM, a few spills, 50 % more
+//                  warps to hide latency with: +8 % env-steps/s at N >= 1 M, -7 % at N = 4096) / 168 (cube tasks: 3)
 #ifndef ARMSIM_SPARSE_MIN_BLOCKS
 #define ARMSIM_SPARSE_MIN_BLOCKS 1
 #endif
+constexpr int BUILD_LATENCY = 0, BUILD_WAVE = 1, BUILD_DENSE = 2;
 constexpr int DENSE_MIN_BLOCKS = 6;
-constexpr int DENSE_MIN_BLOCKS_CUBE = 3;        // push / pick: 223 / 255 registers by default, <= 168 when dense
-constexpr int DENSE_GRID_THRESHOLD = 148 * 4;   // more blocks than one wave of the default reach build
+constexpr int WAVE_MIN_BLOCKS_REACH = 4;
+constexpr int DENSE_MIN_BLOCKS_CUBE = 3;        // push / pick: 227 / 254 registers by default, <= 168 when dense
+constexpr int DENSE_GRID_THRESHOLD = 148 * 4;   // more blocks than one wave of the 128-register reach build
 constexpr int DENSE_GRID_THRESHOLD_CUBE = 148 * 2;
+constexpr int PREFETCH_MAX_GRID = 148;          // one block per SM: the next launch's blocks are resident while this one runs
 
 template <int TASK>
 struct TaskTraits {
@@ -301,18 +309,23 @@ __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.lau
 // own 32 envs (q[7], goal[3], step, 3 action lines; cube tasks: cube[13], last_dist, grip) while the previous launch
 // of the stream is still running; when the state is HBM-cold (a caller cycling through more env batches than L2
 // holds: bench.py's pool, multi-wave N) the round trip is over by the time the loads issue.  L2-hot state: no-op.
+// Only grids of at most one block per SM take it (gridDim.x <= PREFETCH_MAX_GRID): there the next launch's blocks are
+// resident and waiting while this one runs; larger grids start block by block as slots free up, so the prefetch would
+// lead its loads by nothing and only add requests (measured: reach N = 32768 5.1 -> 5.8 us with it).
+
 template <int TASK>
-__device__ __forceinline__ void prefetch_env_lines(const TaskParams& T, const StatePtrs& S, const float* action, int wbase, int lane) {
-  const int n = T.n;
+__device__ __forceinline__ void prefetch_env_lines(int n, const float* q, const float* goal, const int* step, const float* cube,
+                                                       const float* last_dist, const float* grip, const float* action, int wbase,
+                                                       int lane) {
   const void* p = nullptr;
-  if (lane < 7) p = S.q + (size_t)lane * n + wbase;
-  else if (lane < 10) p = S.goal + (size_t)(lane - 7) * n + wbase;
-  else if (lane == 10) p = S.step + wbase;
+  if (lane < 7) p = q + (size_t)lane * n + wbase;
+  else if (lane < 10) p = goal + (size_t)(lane - 7) * n + wbase;
+  else if (lane == 10) p = step + wbase;
   else if (lane < 14) { if (action != nullptr && (wbase * 3 + (lane - 11) * 32) < n * 3) p = action + (size_t)wbase * 3 + (lane - 11) * 32; }
   else if (TaskTraits<TASK>::HAS_CUBE) {
-    if (lane < 27) p = S.cube + (size_t)(lane - 14) * n + wbase;
-    else if (lane == 27) p = S.last_dist + wbase;
-    else if (lane == 28) p = S.grip + wbase;
+    if (lane < 27) p = cube + (size_t)(lane - 14) * n + wbase;
+    else if (lane == 27) p = last_dist + wbase;
+    else if (lane == 28) p = grip + wbase;
   }
   if (p != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -332,9 +345,9 @@ __device__ __forceinline__ void notify_host(const HostNotify& H) {
 // its [32,3] action rows and [32,OBS] observation rows through its own slice of shared memory (row-major caller
 // layout <-> one-value-per-lane), ordered by __syncwarp only -- no block-wide barrier on the device path, so warps
 // never wait for each other's HBM latency.
-template <int TASK, int ROBOT, bool DENSE = false>
-__global__ void __launch_bounds__(LANE_BLOCK, DENSE ? (TaskTraits<TASK>::HAS_CUBE ? DENSE_MIN_BLOCKS_CUBE : DENSE_MIN_BLOCKS)
-                                                    : ARMSIM_SPARSE_MIN_BLOCKS)
+template <int TASK, int ROBOT, int BUILD = BUILD_LATENCY>
+__global__ void __launch_bounds__(LANE_BLOCK, BUILD == BUILD_DENSE ? (TaskTraits<TASK>::HAS_CUBE ? DENSE_MIN_BLOCKS_CUBE : DENSE_MIN_BLOCKS)
+                                              : (BUILD == BUILD_WAVE ? WAVE_MIN_BLOCKS_REACH : ARMSIM_SPARSE_MIN_BLOCKS))
 step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T, const StatePtrs S,
                  const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
                  uint8_t* __restrict__ done, uint8_t* __restrict__ success, float* __restrict__ final_obs,
@@ -344,7 +357,9 @@ step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ 
   __shared__ float s_io[LANE_BLOCK / 32][STAGE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wbase = blockIdx.x * LANE_BLOCK + warp * 32;
-  if (wbase < T.n) prefetch_env_lines<TASK>(T, S, H.flags == nullptr ? action : nullptr, wbase, lane);   // (host path: actions sit in mapped host memory)
+  if (BUILD == BUILD_LATENCY && gridDim.x <= PREFETCH_MAX_GRID && wbase < T.n)
+    prefetch_env_lines<TASK>(T.n, S.q, S.goal, S.step, S.cube, S.last_dist, S.grip, H.flags == nullptr ? action : nullptr, wbase,
+                             lane);   // (host path: actions sit in mapped host memory)
   pdl_wait();
   pdl_release();
   if (wbase < T.n) {
@@ -413,6 +428,15 @@ step_torque_kernel(const __grid_constant__ ChainParams C, const __grid_constant_
   __shared__ float s_io[LANE_BLOCK / 32][32 * OD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wbase = blockIdx.x * LANE_BLOCK + warp * 32;
+  if (gridDim.x <= PREFETCH_MAX_GRID && wbase < T.n) {   // same pre-wait L2 prefetch as the IK kernel: q[7], qd[7], goal[3], step, the 7 torque lines
+    const void* pf = nullptr;
+    if (lane < 7) pf = S.q + (size_t)lane * T.n + wbase;
+    else if (lane < 14) pf = S.qd + (size_t)(lane - 7) * T.n + wbase;
+    else if (lane < 17) pf = S.goal + (size_t)(lane - 14) * T.n + wbase;
+    else if (lane == 17) pf = S.step + wbase;
+    else if (lane < 25 && H.flags == nullptr && (wbase * NJ + (lane - 18) * 32) < T.n * NJ) pf = action + (size_t)wbase * NJ + (lane - 18) * 32;
+    if (pf != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+  }
   pdl_wait();
   pdl_release();
   if (wbase < T.n) {
