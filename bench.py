@@ -12,12 +12,13 @@ Timing hygiene: the 4096-env working set (0.5 MB) would sit in L2, so the bench 
 4096-env batches whose touched state exceeds 2x the 126 MB L2 and steps them round-robin: every launch reads and
 writes HBM-cold state.  Actions: a ring of 61 independent U(-0.7,0.7) sets (coprime with the pool size), so every env
 sees a different action on each of its steps and random-walks through the workspace like under an untrained policy
-(a constant action per env would pin the arms in workspace corners).  The pool is walked INDEPENDENTLY of K: the
-K-launch unit is captured as ceil(pool / K) CUDA graphs that together cover the whole pool, replayed round-robin, so
-consecutive replays never touch the same batches whatever K the caller picks (K = 20 and K = 2000 measure the same
-thing).  `value` is device-timed: after ~0.3 s of untimed replays (clocks up, envs in mid-episode states) R >= 50
-replays are each bracketed by a CUDA event pair on the launching stream, the whole set bracketed by a barrier +
-synchronize; per rank the MEDIAN replay time counts (p10 / p90 are printed too), max over ranks.  `e2e` is the same
+(a constant action per env would pin the arms in workspace corners).  The pool is walked INDEPENDENTLY of K: the timed
+unit -- exactly K launches between two event-record nodes -- is laid out INSIDE CUDA graphs that together cover the whole
+pool, so consecutive replays never touch the same batches whatever K the caller picks, and the boundary events sit on a
+side branch of the graph so that the launches keep their kernel-to-kernel chain across unit boundaries (K = 20 and
+K = 2000 measure the same thing to ~1 %; capture_timed_units).  `value` is device-timed: after ~0.3 s of untimed replays
+(clocks up, envs in mid-episode states) >= 60 unit intervals are collected, the whole set bracketed by a barrier +
+synchronize; per rank the MEDIAN interval counts (p10 / p90 are printed too), max over ranks.  `e2e` is the same
 metric through the host-buffer C-ABI call (armsim_step_host on the handle's pinned block: the kernel reads the actions
 from / writes the results to host memory over PCIe every step, the host polls per-block doorbells), timed on the host
 clock as R repeats of a K-step loop, median.
@@ -237,31 +238,45 @@ def capture_pool_graphs(torch, envs, actions, steps, stream, first=0):
     return graphs
 
 
-def capture_timed_units(torch, envs, actions, steps, stream, first=0):
-    """The headline measurement: CUDA graphs made of timed UNITS laid back to back, one unit = [event record node |
-    exactly K fused-step launches | event record node, shared with the next unit] (torch.cuda.Event(external=True) records become graph nodes).
-    Inside a graph the units follow each other kernel-to-kernel, so a unit's interval contains K launches and nothing
-    else -- no graph-launch front-end latency, which at K = 20 is ~7 % of a replay timed from outside (measured, first
-    r02 runs) and made the number depend on K.  A graph holds U = clamp(6000 // K, 1, 60) units; as many graphs are
-    captured as it takes to walk the whole pool."""
+def capture_timed_units(torch, envs, actions, steps, stream, first=0, side_events=True):
+    """The headline measurement: CUDA graphs made of timed UNITS laid back to back, one unit = exactly K fused-step
+    launches between two event-record nodes (torch.cuda.Event(external=True) records become graph nodes; consecutive
+    units share their boundary event).  Inside a graph the units follow each other kernel-to-kernel, so a unit's
+    interval contains K launches and nothing else -- no graph-launch front-end latency, which at K = 20 is ~7 % of a
+    replay timed from outside.  side_events=True: the boundary events are recorded on a SIDE branch of the graph (a
+    second captured stream that waits for the unit's last launch), so the record node is a leaf and the launches keep
+    their kernel-to-kernel programmatic-dependent-launch chain across unit boundaries -- each interval runs from the
+    completion of one unit's last launch to the completion of the next unit's last launch, exactly K launches of steady
+    state, whatever K is; with the record node IN the chain every unit pays one un-overlapped launch ramp (0.29 us per
+    step at K = 20).  A graph holds U = clamp(6000 // K, 1, 60) units; as many graphs are captured as it takes to walk
+    the whole pool."""
     pool, na = len(envs), len(actions)
     units = max(1, min(60, 6000 // steps))
     n_graphs = max(1, -(-pool // (units * steps)))
     graphs = []
     j = first
+    side = torch.cuda.Stream(device=stream.device) if side_events else None
     for g in range(n_graphs):
-        # consecutive units SHARE their boundary event: [E0 | K launches | E1 | K launches | E2 ...] -- an interval
-        # E_u -> E_u+1 still holds exactly K launches, but only ONE event node (not two) interrupts the kernel-to-kernel
-        # (programmatic dependent launch) chain per unit, which is what makes K = 20 read like K = 2000
         marks = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(units + 1)]
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=stream):
-            marks[0].record(stream)
+            def mark(ev):
+                if side is None:
+                    ev.record(stream)
+                else:
+                    side.wait_stream(stream)
+                    ev.record(side)
+            # one untimed launch first, so that the opening mark also sits behind a launch of the chain
+            envs[j % pool].step(actions[j % na])
+            j += 1
+            mark(marks[0])
             for u in range(units):
                 for _ in range(steps):
                     envs[j % pool].step(actions[j % na])
                     j += 1
-                marks[u + 1].record(stream)
+                mark(marks[u + 1])
+            if side is not None:
+                stream.wait_stream(side)
         graphs.append((gr, list(zip(marks[:-1], marks[1:]))))
     return graphs
 
@@ -365,14 +380,21 @@ def run_ours(args):
         for k in range(max(warmup, 3)):                         # eager warm-up (also first-use init)
             envs[k % pool].step(actions[k % len(actions)])
     stream.synchronize()
+    timed_units, side_events = True, os.environ.get("BENCH_INLINE_EVENTS", "0") != "1"
     try:
-        graphs = capture_timed_units(torch, envs, actions, steps, stream, first=max(warmup, 3))
-        timed_units = True
-    except Exception:          # no external-event support: time whole replays from outside instead
-        graphs = capture_pool_graphs(torch, envs, actions, steps, stream, first=max(warmup, 3))
-        timed_units = False
+        graphs = capture_timed_units(torch, envs, actions, steps, stream, first=max(warmup, 3), side_events=side_events)
+    except Exception:
+        stream.synchronize()
+        launches0 = sum(e.launch_count for e in envs) - max(warmup, 3)
+        try:                   # boundary events in the launch chain instead of on a side branch
+            side_events = False
+            graphs = capture_timed_units(torch, envs, actions, steps, stream, first=max(warmup, 3), side_events=False)
+        except Exception:      # no external-event support: time whole replays from outside instead
+            launches0 = sum(e.launch_count for e in envs) - max(warmup, 3)
+            graphs = capture_pool_graphs(torch, envs, actions, steps, stream, first=max(warmup, 3))
+            timed_units = False
     cap_launches = sum(e.launch_count for e in envs) - launches0 - max(warmup, 3)
-    assert cap_launches % steps == 0
+    assert (cap_launches - (len(graphs) if timed_units else 0)) % steps == 0      # (+ one untimed lead-in launch per unit graph)
 
     def barrier():
         if world > 1:
@@ -481,8 +503,10 @@ def run_ours(args):
                                   "timed replay (outside the event pair): a random walk, no env ever repeats an action; auto-reset in kernel" % (N_ACT, N_ACT),
                        "l2": "inputs larger than L2: round-robin over a pool of %d independent %d-env batches "
                              "(%.0f MB touched state, L2 = 126 MB), every launch HBM-cold" % (pool, n, pool * abytes * n / 1e6),
-                       "launch": ("CUDA graphs of timed units, one unit = [event record | exactly K fused-step launches | event record] "
-                                  "(%d graph(s) x %d units covering the pool)" % (len(graphs), len(graphs[0][1]))) if timed_units else
+                       "launch": ("CUDA graphs of timed units, one unit = exactly K fused-step launches between two event-record nodes "
+                                  "(%s); %d graph(s) x %d units covering the pool"
+                                  % ("records on a side branch of the graph: the launches keep their kernel-to-kernel chain across unit "
+                                     "boundaries" if side_events else "records in the launch chain", len(graphs), len(graphs[0][1]))) if timed_units else
                                  ("CUDA graphs of exactly K fused-step launches each (%d graphs covering the pool, replayed round-robin), "
                                   "CUDA event pair per replay on the launching stream" % len(graphs))},
             "timing": {"repeats": REPEATS, "statistic": "median over the timed replays, max over ranks",
