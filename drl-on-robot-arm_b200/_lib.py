@@ -25,7 +25,7 @@ EXPORTS = [
     "armsim_abi_version", "armsim_last_error", "armsim_default_config", "armsim_create", "armsim_destroy",
     "armsim_reset", "armsim_step", "armsim_step_host", "armsim_reset_host", "armsim_set_state", "armsim_get_state",
     "armsim_obs_dim", "armsim_action_dim", "armsim_n_envs", "armsim_mapping", "armsim_launch_count", "armsim_fk_host",
-    "armsim_host_buffers", "armsim_step_ex", "armsim_step_tracked", "armsim_step_host_async", "armsim_step_host_wait",
+    "armsim_host_buffers", "armsim_host_server", "armsim_step_ex", "armsim_step_tracked", "armsim_step_host_async", "armsim_step_host_wait",
     "armsim_explore", "armsim_policy_act", "armsim_track_episodes", "armsim_episode_stats", "armsim_set_episode_stats",
     "armsim_replay_create", "armsim_replay_destroy", "armsim_replay_begin", "armsim_replay_store", "armsim_replay_sample",
     "armsim_replay_gather", "armsim_replay_info", "armsim_replay_table", "armsim_replay_last_error",
@@ -97,6 +97,7 @@ def lib():
     L.armsim_step_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.armsim_step_tracked.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.armsim_step_host_async.argtypes = [vp, vp]
+    L.armsim_host_server.argtypes = [vp, i32]
     L.armsim_explore.argtypes = [vp, vp, C.c_float, C.c_float, vp, vp]
     L.armsim_policy_act.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp]
     L.armsim_track_episodes.argtypes = [vp, vp, vp, vp, vp]

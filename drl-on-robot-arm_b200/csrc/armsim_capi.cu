@@ -67,6 +67,13 @@ struct ArmSim {
   cudaGraphExec_t host_graph = nullptr;   // the zero-copy host step as an instantiated graph (parameters never change)
   bool host_graph_tried = false;
   bool host_pending = false;              // armsim_step_host_async issued, armsim_step_host_wait not yet
+  // resident step server (armsim_host_server): the kernel stays on the GPU between host steps
+  bool server_enabled = false, server_live = false;
+  unsigned long long server_idle_ns = 0;
+  volatile unsigned int* h_cmd = nullptr;    // mapped host word: sequence number of the step requested, or SERVER_STOP
+  unsigned int* d_relay = nullptr;           // device word through which block 0 republishes h_cmd
+  unsigned int* h_relay_init = nullptr;      // pinned staging word for resetting d_relay
+  double server_last_use = 0.0;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   float* fk_scratch = nullptr;   // armsim_fk_host staging (q | pos | rot), grown on demand
@@ -248,6 +255,7 @@ int64_t armsim_launch_count(const ArmSim* s) { return s ? s->launches : ARMSIM_E
 void armsim_destroy(ArmSim* s) {
   if (!s) return;
   cudaSetDevice(s->cfg.device);
+  if (s->server_live && s->h_cmd) __atomic_store_n((unsigned int*)s->h_cmd, 0xffffffffu, __ATOMIC_RELEASE);   // SERVER_STOP
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->state_block) cudaFree(s->state_block);
   if (s->d_io) cudaFree(s->d_io);
@@ -433,16 +441,19 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   if (cudaMalloc((void**)&s->d_io, s->act_bytes + s->out_bytes) != cudaSuccess ||
       cudaMalloc((void**)&s->d_stats, 3 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(s->d_stats, 0, 3 * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMalloc((void**)&s->d_cta_seq, flag_bytes) != cudaSuccess ||
-      cudaMemset(s->d_cta_seq, 0, flag_bytes) != cudaSuccess ||
-      cudaHostAlloc((void**)&s->h_pin, s->act_bytes + s->out_bytes + flag_bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+      cudaMalloc((void**)&s->d_cta_seq, flag_bytes + 256) != cudaSuccess ||
+      cudaMemset(s->d_cta_seq, 0, flag_bytes + 256) != cudaSuccess ||
+      cudaHostAlloc((void**)&s->h_pin, s->act_bytes + s->out_bytes + flag_bytes + 512, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
       cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     armsim_destroy(s);
     return fail(ARMSIM_E_NOMEM, "armsim_create: staging allocation failed");
   }
   s->h_flags = (volatile unsigned int*)(s->h_pin + s->act_bytes + s->out_bytes);
-  memset((void*)s->h_flags, 0, flag_bytes);
+  memset((void*)s->h_flags, 0, flag_bytes + 512);
+  s->h_cmd = (volatile unsigned int*)(s->h_pin + s->act_bytes + s->out_bytes + flag_bytes);
+  s->h_relay_init = (unsigned int*)(s->h_pin + s->act_bytes + s->out_bytes + flag_bytes + 256);
+  s->d_relay = (unsigned int*)((char*)s->d_cta_seq + flag_bytes);
   int rc = launch_reset(s, nullptr, nullptr, s->stream);
   if (rc == ARMSIM_OK && cudaStreamSynchronize(s->stream) != cudaSuccess) rc = fail(ARMSIM_E_CUDA, "armsim_create: initial reset failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (rc != ARMSIM_OK) { armsim_destroy(s); return rc; }
@@ -450,8 +461,17 @@ int armsim_create(const ArmsimConfig* cfg, ArmSim** out) {
   return ARMSIM_OK;
 }
 
+static int server_launch(ArmSim* s);
+static int server_quiesce(ArmSim* s);
+#define ARMSIM_QUIESCE(s)                   \
+  do {                                      \
+    int _q = server_quiesce(s);             \
+    if (_q) return _q;                      \
+  } while (0)
+
 int armsim_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_reset: null handle");
+  ARMSIM_QUIESCE(s);
   DeviceGuard guard(s->cfg.device);
   return launch_reset(s, mask_dev, obs_dev, (cudaStream_t)stream);
 }
@@ -459,6 +479,7 @@ int armsim_reset(ArmSim* s, const uint8_t* mask_dev, float* obs_dev, void* strea
 int armsim_step(ArmSim* s, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev,
                 void* stream) {
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_step: null handle");
+  ARMSIM_QUIESCE(s);
   if (!action_dev || !obs_dev || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_step: null buffer");
   DeviceGuard guard(s->cfg.device);
   return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream);
@@ -486,7 +507,14 @@ static int wait_doorbells(ArmSim* s, unsigned int seq) {
       if (q == cudaSuccess) {
         while (b < grid && f[b] == seq) ++b;
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
-        return b == grid ? ARMSIM_OK : fail(ARMSIM_E_CUDA, "armsim_step_host: kernel finished without ringing every doorbell");
+        if (b == grid) return ARMSIM_OK;
+        if (s->server_enabled) {        // the resident kernel timed out with this command (partly) unserved: start it again
+          s->server_live = false;
+          int rc = server_launch(s);
+          if (rc) return rc;
+          continue;
+        }
+        return fail(ARMSIM_E_CUDA, "armsim_step_host: kernel finished without ringing every doorbell");
       }
       if (q != cudaErrorNotReady) return fail(ARMSIM_E_CUDA, "armsim_step_host: %s", cudaGetErrorString(q));
     }
@@ -507,6 +535,7 @@ int armsim_host_buffers(ArmSim* s, float** action, float** obs, float** reward, 
 int armsim_step_ex(ArmSim* s, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev,
                    float* final_obs_dev, void* stream) {
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_ex: null handle");
+  ARMSIM_QUIESCE(s);
   if (!action_dev || !obs_dev || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_step_ex: null buffer");
   DeviceGuard guard(s->cfg.device);
   return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream, HostNotify{nullptr, nullptr},
@@ -516,12 +545,86 @@ int armsim_step_ex(ArmSim* s, const float* action_dev, float* obs_dev, float* re
 int armsim_step_tracked(ArmSim* s, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                         uint8_t* success_dev, float* final_obs_dev, void* stream) {
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_step_tracked: null handle");
+  ARMSIM_QUIESCE(s);
   if (!action_dev || !obs_dev || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_step_tracked: null buffer");
   if (s->cfg.mode == ARMSIM_MODE_TORQUE) return fail(ARMSIM_E_INVALID, "armsim_step_tracked: IK-teleport mode only (use armsim_step_ex + armsim_track_episodes)");
   DeviceGuard guard(s->cfg.device);
   HostNotify H{nullptr, nullptr};
   H.track_stats = s->d_stats;
   return launch_step(s, action_dev, obs_dev, reward_dev, done_dev, success_dev, (cudaStream_t)stream, H, final_obs_dev);
+}
+
+// ---------------------------------------------------------------------------------------------- resident step server
+static double now_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+#define ARMSIM_SERVER_CASE(TASK, ROBOT)                                                                                  \
+  case (TASK) * 4 + (ROBOT):                                                                                             \
+    ensure_smem(step_server_kernel<TASK, ROBOT>, task_smem<TASK>());                                                     \
+    step_server_kernel<TASK, ROBOT><<<s->grid, LANE_BLOCK, task_smem<TASK>(), s->stream>>>(s->chain, s->task, s->S, (const float*)s->h_pin, o, r, d, su, H, ctl); \
+    break;
+
+// Put the resident kernel on the handle's stream.  Blocks resume from their completed-step counters (d_cta_seq), so a
+// command that was pending when the previous instance timed out runs exactly once.
+static int server_launch(ArmSim* s) {
+  char* h_out = s->h_pin + s->act_bytes;
+  float* o = (float*)(h_out + s->off_obs);
+  float* r = (float*)(h_out + s->off_reward);
+  uint8_t *d = (uint8_t*)(h_out + s->off_done), *su = (uint8_t*)(h_out + s->off_success);
+  HostNotify H{s->d_cta_seq, (unsigned int*)s->h_flags};
+  ServerCtl ctl{s->h_cmd, s->d_relay, s->server_idle_ns};
+  if (*s->h_cmd == SERVER_STOP) *s->h_cmd = s->seq;
+  *s->h_relay_init = 0u;                                   // "nothing requested yet" for every block (sequence numbers start at 1)
+  CU(cudaMemcpyAsync(s->d_relay, s->h_relay_init, sizeof(unsigned int), cudaMemcpyHostToDevice, s->stream));
+  switch (s->cfg.task * 4 + s->cfg.robot) {
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_KUKA_IIWA)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_DIANA_S1)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_REACH, ARMSIM_ROBOT_CUSTOM)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_PUSH, ARMSIM_ROBOT_KUKA_IIWA)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_PUSH, ARMSIM_ROBOT_DIANA_S1)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_PUSH, ARMSIM_ROBOT_CUSTOM)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_PICK, ARMSIM_ROBOT_KUKA_IIWA)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_PICK, ARMSIM_ROBOT_DIANA_S1)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_PICK, ARMSIM_ROBOT_CUSTOM)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_KUKA_IIWA)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_DIANA_S1)
+    ARMSIM_SERVER_CASE(ARMSIM_TASK_KUKA_REACH, ARMSIM_ROBOT_CUSTOM)
+    default: return fail(ARMSIM_E_INVALID, "bad task / robot");
+  }
+  CU(cudaGetLastError());
+  s->launches += 1;
+  s->server_live = true;
+  s->server_last_use = now_s();
+  return ARMSIM_OK;
+}
+
+// Make the resident kernel leave (every entry point that touches the handle's device state outside the host step calls
+// this first).  Cheap when no server is running.
+static int server_quiesce(ArmSim* s) {
+  if (!s->server_live) return ARMSIM_OK;
+  if (s->host_pending) return fail(ARMSIM_E_STATE, "a host step is in flight: call armsim_step_host_wait first");
+  __atomic_store_n((unsigned int*)s->h_cmd, SERVER_STOP, __ATOMIC_RELEASE);
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  s->server_live = false;
+  __atomic_store_n((unsigned int*)s->h_cmd, s->seq, __ATOMIC_RELEASE);
+  if (e != cudaSuccess) return fail(ARMSIM_E_CUDA, "step server: %s", cudaGetErrorString(e));
+  return ARMSIM_OK;
+}
+
+int armsim_host_server(ArmSim* s, int32_t idle_us) {
+  if (!s) return fail(ARMSIM_E_INVALID, "armsim_host_server: null handle");
+  if (idle_us < 0 || idle_us > 1000000) return fail(ARMSIM_E_INVALID, "armsim_host_server: idle_us must be in [0, 1000000]");
+  if (idle_us > 0 && (!s->zero_copy || s->cfg.mode != ARMSIM_MODE_IK_TELEPORT))
+    return fail(ARMSIM_E_INVALID, "armsim_host_server: needs the zero-copy host path (n_envs <= 65536) in IK-teleport mode");
+  DeviceGuard guard(s->cfg.device);
+  int rc = server_quiesce(s);
+  if (rc) return rc;
+  s->server_enabled = idle_us > 0;
+  s->server_idle_ns = (unsigned long long)idle_us * 1000ull;
+  return ARMSIM_OK;
 }
 
 // First half of the host step: stage the actions (unless they already sit in the pinned block) and put the fused
@@ -533,7 +636,20 @@ static int host_step_submit(ArmSim* s, const float* action_host) {
   if (s->host_pending) return fail(ARMSIM_E_STATE, "armsim_step_host_async: the previous step has not been waited for");
   // callers that work in the handle's own pinned block (armsim_host_buffers) skip the staging memcpys
   if ((const char*)action_host != s->h_pin) memcpy(s->h_pin, action_host, n * s->act_dim * 4);
-  if (s->zero_copy) {
+  if (s->zero_copy && s->server_enabled) {
+    // resident kernel: no CUDA call on the fast path -- one release store of the step's sequence number
+    const double t = now_s();
+    if (!s->server_live || (t - s->server_last_use) * 1e9 > 0.5 * (double)s->server_idle_ns) {
+      if (s->server_live && cudaStreamQuery(s->stream) == cudaSuccess) s->server_live = false;   // it timed out meanwhile
+      if (!s->server_live) {
+        int rc = server_launch(s);
+        if (rc) return rc;
+      }
+    }
+    s->server_last_use = t;
+    ++s->seq;
+    __atomic_store_n((unsigned int*)s->h_cmd, s->seq, __ATOMIC_RELEASE);
+  } else if (s->zero_copy) {
     HostNotify H{s->d_cta_seq, (unsigned int*)s->h_flags};
     float* o = (float*)(h_out + s->off_obs);
     float* r = (float*)(h_out + s->off_reward);
@@ -616,6 +732,7 @@ int armsim_step_host_wait(ArmSim* s, float* obs_host, float* reward_host, uint8_
 
 int armsim_explore(ArmSim* s, const float* actor_out_dev, float noise_std, float clip, float* action_out_dev, void* stream) {
   if (!s || !actor_out_dev || !action_out_dev) return fail(ARMSIM_E_INVALID, "armsim_explore: null argument");
+  ARMSIM_QUIESCE(s);
   if (!(noise_std >= 0.0f)) return fail(ARMSIM_E_INVALID, "armsim_explore: noise_std must be >= 0");
   DeviceGuard guard(s->cfg.device);
   explore_kernel<<<s->grid, LANE_BLOCK, 0, (cudaStream_t)stream>>>(s->task, s->S, s->act_dim, actor_out_dev, noise_std, clip, action_out_dev);
@@ -628,6 +745,7 @@ int armsim_policy_act(ArmSim* s, const float* obs_dev, const float* w1, const fl
                       const float* w3, const float* b3, int32_t hidden, float action_bound, float noise_std, float clip,
                       float* action_out_dev, void* stream) {
   if (!s || !obs_dev || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !action_out_dev) return fail(ARMSIM_E_INVALID, "armsim_policy_act: null argument");
+  ARMSIM_QUIESCE(s);
   if (hidden != POLICY_H) return fail(ARMSIM_E_INVALID, "armsim_policy_act: hidden must be %d (got %d)", POLICY_H, hidden);
   if (s->obs_dim > POLICY_MAX_S || s->act_dim > POLICY_MAX_A) return fail(ARMSIM_E_INVALID, "armsim_policy_act: obs_dim %d / action_dim %d too wide", s->obs_dim, s->act_dim);
   DeviceGuard guard(s->cfg.device);
@@ -647,6 +765,7 @@ int armsim_policy_act(ArmSim* s, const float* obs_dev, const float* w1, const fl
 
 int armsim_track_episodes(ArmSim* s, const float* reward_dev, const uint8_t* done_dev, const uint8_t* success_dev, void* stream) {
   if (!s || !reward_dev || !done_dev || !success_dev) return fail(ARMSIM_E_INVALID, "armsim_track_episodes: null argument");
+  ARMSIM_QUIESCE(s);
   DeviceGuard guard(s->cfg.device);
   track_episodes_kernel<<<s->grid, LANE_BLOCK, 0, (cudaStream_t)stream>>>(s->n, s->S, reward_dev, done_dev, success_dev, s->d_stats);
   s->launches += 1;
@@ -656,6 +775,7 @@ int armsim_track_episodes(ArmSim* s, const float* reward_dev, const uint8_t* don
 
 int armsim_episode_stats(ArmSim* s, double out[3]) {
   if (!s || !out) return fail(ARMSIM_E_INVALID, "armsim_episode_stats: null argument");
+  ARMSIM_QUIESCE(s);
   CU(cudaSetDevice(s->cfg.device));
   unsigned long long h[3];
   CU(cudaDeviceSynchronize());
@@ -668,6 +788,7 @@ int armsim_episode_stats(ArmSim* s, double out[3]) {
 
 int armsim_set_episode_stats(ArmSim* s, const double in[3]) {
   if (!s || !in) return fail(ARMSIM_E_INVALID, "armsim_set_episode_stats: null argument");
+  ARMSIM_QUIESCE(s);
   CU(cudaSetDevice(s->cfg.device));
   const unsigned long long h[3] = {(unsigned long long)llround(in[0]), (unsigned long long)llround(in[1]),
                                    (unsigned long long)llround(in[2] * 65536.0)};
@@ -678,6 +799,7 @@ int armsim_set_episode_stats(ArmSim* s, const double in[3]) {
 
 int armsim_reset_host(ArmSim* s, const uint8_t* mask_host, float* obs_host) {
   if (!s) return fail(ARMSIM_E_INVALID, "armsim_reset_host: null handle");
+  ARMSIM_QUIESCE(s);
   CU(cudaSetDevice(s->cfg.device));
   const size_t n = (size_t)s->n;
   char* h_out = s->h_pin + s->act_bytes;
@@ -703,6 +825,7 @@ int armsim_reset_host(ArmSim* s, const uint8_t* mask_host, float* obs_host) {
 
 int armsim_set_state(ArmSim* s, int32_t field, const void* host_src, size_t bytes) {
   if (!s || !host_src) return fail(ARMSIM_E_INVALID, "armsim_set_state: null argument");
+  ARMSIM_QUIESCE(s);
   const int w = field_width(field);
   if (w < 0 || field == ARMSIM_F_IK_ITERS) return fail(ARMSIM_E_STATE, "armsim_set_state: field %d not writable", field);
   const size_t n = (size_t)s->n;
@@ -720,6 +843,7 @@ int armsim_set_state(ArmSim* s, int32_t field, const void* host_src, size_t byte
 
 int armsim_get_state(ArmSim* s, int32_t field, void* host_dst, size_t bytes) {
   if (!s || !host_dst) return fail(ARMSIM_E_INVALID, "armsim_get_state: null argument");
+  ARMSIM_QUIESCE(s);
   const int w = field_width(field);
   if (w < 0) return fail(ARMSIM_E_STATE, "armsim_get_state: unknown field %d", field);
   const size_t n = (size_t)s->n;
@@ -736,6 +860,7 @@ int armsim_get_state(ArmSim* s, int32_t field, void* host_dst, size_t bytes) {
 
 int armsim_fk_host(ArmSim* s, const float* q_host, int32_t n, float* pos_host, float* rot_host) {
   if (!s || !q_host || !pos_host || n <= 0) return fail(ARMSIM_E_INVALID, "armsim_fk_host: bad argument");
+  ARMSIM_QUIESCE(s);
   CU(cudaSetDevice(s->cfg.device));
   if (n > s->fk_cap) {                       // persistent staging: the Env shims call this on every first reset()
     if (s->fk_scratch) cudaFree(s->fk_scratch);

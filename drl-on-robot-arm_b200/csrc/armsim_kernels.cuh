@@ -341,10 +341,68 @@ __device__ __forceinline__ void notify_host(const HostNotify& H) {
   }
 }
 
-// One launch = Env.step() of the whole batch.  Each warp owns 32 consecutive envs and is self-contained: it stages
-// its [32,3] action rows and [32,OBS] observation rows through its own slice of shared memory (row-major caller
-// layout <-> one-value-per-lane), ordered by __syncwarp only -- no block-wide barrier on the device path, so warps
-// never wait for each other's HBM latency.
+// Env.step() of the 32 envs one warp owns.  Each warp is self-contained: it stages its [32,3] action rows and
+// [32,OBS] observation rows through its own slice of shared memory (row-major caller layout <-> one-value-per-lane),
+// ordered by __syncwarp only -- no block-wide barrier on the device path, so warps never wait for each other's HBM
+// latency.  COHERENT_ACTIONS: the actions are re-read from mapped host memory by a RESIDENT kernel (step_server_kernel)
+// and must not come out of a non-coherent cache.
+template <int TASK, int ROBOT, bool COHERENT_ACTIONS>
+__device__ __forceinline__ void step_warp(const ChainParams& C, const TaskParams& T, const StatePtrs& S,
+                                          const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
+                                          uint8_t* __restrict__ done, uint8_t* __restrict__ success, float* __restrict__ final_obs,
+                                          const HostNotify& H, float* st, int wbase, int lane) {
+  constexpr int OD = TaskTraits<TASK>::OBS;
+  const int cnt = min(32, T.n - wbase);
+  const bool live = lane < cnt;
+  const int e = wbase + min(lane, cnt - 1);
+
+  float araw[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = k * 32 + lane;
+    if (COHERENT_ACTIONS) araw[k] = i < cnt * 3 ? *(const volatile float*)(action + (size_t)wbase * 3 + i) : 0.f;
+    else araw[k] = i < cnt * 3 ? __ldg(action + (size_t)wbase * 3 + i) : 0.f;
+  }
+  EnvRegs<TASK> E;
+  load_env<TASK>(T, S, e, E);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) st[k * 32 + lane] = araw[k];
+  __syncwarp();
+  const int al = min(lane, cnt - 1) * 3;
+  const float a[3] = {st[al], st[al + 1], st[al + 2]};
+  __syncwarp();
+
+  float o[OD], of[OD], r;
+  uint8_t d, su;
+  step_env<TASK, ROBOT>(C, T, S, e, live, E, a, o, of, r, d, su);
+  if (live) {
+    reward[e] = r;
+    done[e] = d;
+    success[e] = su;
+  }
+  if (H.track_stats != nullptr) track_warp(S, e, live, r, d != 0, su != 0, H.track_stats);
+#pragma unroll
+  for (int k = 0; k < OD; ++k) st[lane * OD + k] = o[k];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < OD; ++k) {
+    const int i = k * 32 + lane;
+    if (i < cnt * OD) obs[(size_t)wbase * OD + i] = st[i];
+  }
+  if (final_obs != nullptr) {        // second pass through the same staging slice
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < OD; ++k) st[lane * OD + k] = of[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < OD; ++k) {
+      const int i = k * 32 + lane;
+      if (i < cnt * OD) final_obs[(size_t)wbase * OD + i] = st[i];
+    }
+  }
+}
+
+// One launch = Env.step() of the whole batch.
 template <int TASK, int ROBOT, int BUILD = BUILD_LATENCY>
 __global__ void __launch_bounds__(LANE_BLOCK, BUILD == BUILD_DENSE ? (TaskTraits<TASK>::HAS_CUBE ? DENSE_MIN_BLOCKS_CUBE : DENSE_MIN_BLOCKS)
                                               : (BUILD == BUILD_WAVE ? WAVE_MIN_BLOCKS_REACH : ARMSIM_SPARSE_MIN_BLOCKS))
@@ -362,57 +420,70 @@ step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ 
                              lane);   // (host path: actions sit in mapped host memory)
   pdl_wait();
   pdl_release();
-  if (wbase < T.n) {
-    const int cnt = min(32, T.n - wbase);
-    const bool live = lane < cnt;
-    const int e = wbase + min(lane, cnt - 1);
-    float* st = s_io[warp];
-
-    float araw[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int i = k * 32 + lane;
-      araw[k] = i < cnt * 3 ? __ldg(action + (size_t)wbase * 3 + i) : 0.f;
-    }
-    EnvRegs<TASK> E;
-    load_env<TASK>(T, S, e, E);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) st[k * 32 + lane] = araw[k];
-    __syncwarp();
-    const int al = min(lane, cnt - 1) * 3;
-    const float a[3] = {st[al], st[al + 1], st[al + 2]};
-    __syncwarp();
-
-    float o[OD], of[OD], r;
-    uint8_t d, su;
-    step_env<TASK, ROBOT>(C, T, S, e, live, E, a, o, of, r, d, su);
-    if (live) {
-      reward[e] = r;
-      done[e] = d;
-      success[e] = su;
-    }
-    if (H.track_stats != nullptr) track_warp(S, e, live, r, d != 0, su != 0, H.track_stats);
-#pragma unroll
-    for (int k = 0; k < OD; ++k) st[lane * OD + k] = o[k];
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < OD; ++k) {
-      const int i = k * 32 + lane;
-      if (i < cnt * OD) obs[(size_t)wbase * OD + i] = st[i];
-    }
-    if (final_obs != nullptr) {        // second pass through the same staging slice
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < OD; ++k) st[lane * OD + k] = of[k];
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < OD; ++k) {
-        const int i = k * 32 + lane;
-        if (i < cnt * OD) final_obs[(size_t)wbase * OD + i] = st[i];
-      }
-    }
-  }
+  if (wbase < T.n) step_warp<TASK, ROBOT, false>(C, T, S, action, obs, reward, done, success, final_obs, H, s_io[warp], wbase, lane);
   notify_host(H);
+}
+
+// The resident form of the host step (armsim_host_server): the same Env.step(), but the kernel stays on the GPU and
+// serves one step per command instead of being launched per step -- a launch-per-step host call spends ~12 of its ~18 us
+// between cudaGraphLaunch and the kernel's first instruction.  Protocol (tools/e2e_breakdown.cu measured the
+// alternatives: 32 blocks polling host memory themselves take 98 us per round trip, one poller + a device relay 7):
+//   host:    writes the actions into the pinned block, then the step's sequence number into the mapped word `cmd`
+//   block 0: thread 0 polls `cmd` over PCIe and republishes it in the device word `relay`; the other blocks poll that
+//   blocks:  a block runs step number cta_seq[b] + 1 when the relayed number has reached it, rings its doorbell as in the
+//            launched path (notify_host: the host waits for gridDim.x doorbells), and goes back to polling
+//   exit:    SERVER_STOP in `cmd`, or no command for idle_ns (block 0 then relays the stop) -- the kernel can never
+//            outlive its idle time-out, and the host relaunches it on the next step (cta_seq persists, so no step runs twice)
+struct ServerCtl {
+  const volatile unsigned int* cmd;     // mapped host memory
+  volatile unsigned int* relay;         // device memory
+  unsigned long long idle_ns;
+};
+constexpr unsigned int SERVER_STOP = 0xffffffffu;
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int TASK, int ROBOT>
+__global__ void __launch_bounds__(LANE_BLOCK, 1)
+step_server_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ TaskParams T, const StatePtrs S,
+                   const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
+                   uint8_t* __restrict__ done, uint8_t* __restrict__ success, const HostNotify H, const ServerCtl ctl) {
+  constexpr int OD = TaskTraits<TASK>::OBS;
+  constexpr int STAGE = 32 * (OD > 3 ? OD : 3);
+  __shared__ float s_io[LANE_BLOCK / 32][STAGE];
+  __shared__ unsigned int s_cmd;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wbase = blockIdx.x * LANE_BLOCK + warp * 32;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      const unsigned int have = H.cta_seq[blockIdx.x];                    // steps this block has completed
+      const unsigned long long t0 = global_ns();
+      unsigned int v;
+      if (blockIdx.x == 0) {
+        for (unsigned int polls = 0;; ++polls) {
+          v = *ctl.cmd;
+          if (v == SERVER_STOP || (int)(v - have) > 0) break;
+          if (global_ns() - t0 > ctl.idle_ns || polls > 50000000u) { v = SERVER_STOP; break; }   // (second bound: belt and braces)
+        }
+        *ctl.relay = v;
+      } else {
+        for (unsigned int polls = 0;; ++polls) {
+          v = *ctl.relay;
+          if (v == SERVER_STOP || (int)(v - have) > 0) break;
+          if (global_ns() - t0 > 2ull * ctl.idle_ns + 1000000ull || polls > 200000000u) { v = SERVER_STOP; break; }   // (block 0 relays its own time-out first)
+        }
+      }
+      s_cmd = v;
+    }
+    __syncthreads();
+    if (s_cmd == SERVER_STOP) return;
+    if (wbase < T.n) step_warp<TASK, ROBOT, true>(C, T, S, action, obs, reward, done, success, nullptr, H, s_io[warp], wbase, lane);
+    notify_host(H);      // barrier (every thread has read s_cmd by now), then thread 0: cta_seq[b] += 1, system fence, doorbell
+  }
 }
 
 // Torque mode: one launch = one dynamics step of the whole batch.  action [n,7] joint torques; obs [n, OBS+14] = the

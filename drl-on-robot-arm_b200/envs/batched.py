@@ -46,6 +46,12 @@ class ArmSimHandle:
         self.act_dim = L.lib().armsim_action_dim(h)
         self.task = task_id
 
+    def host_server(self, idle_us=20000):
+        """keep ONE kernel resident for the host-buffer step (armsim_host_server): step_host / step_pinned / step_async then
+        cost a release store + a doorbell poll instead of a launch.  idle_us = 0 turns it off.  Any other call on this
+        handle makes the resident kernel leave first; it also leaves by itself after idle_us without a step."""
+        L.check(L.lib().armsim_host_server(self.h, int(idle_us)))
+
     @property
     def mapping(self):
         """resolved thread mapping of the step kernel ("lane": one CUDA lane per arm; see include/armsim.h)"""

@@ -170,6 +170,16 @@ int armsim_reset_host(ArmSim* sim, const uint8_t* mask_host, float* obs_host);
 int armsim_step_host_async(ArmSim* sim, const float* action_host);
 int armsim_step_host_wait(ArmSim* sim, float* obs_host, float* reward_host, uint8_t* done_host, uint8_t* success_host);
 
+/* Resident step server for the host path (off by default).  idle_us > 0: armsim_step_host / _async stop launching a
+ * kernel per step; ONE kernel stays on the GPU, block 0 polls a command word in the handle's pinned block, every block
+ * serves the step and rings its doorbell, and the kernel leaves by itself after idle_us microseconds without a command
+ * (the next host step starts it again; no step is ever run twice or skipped).  Saves the launch -> first-instruction
+ * latency that dominates a launch-per-step host call.  While the server is alive any OTHER entry point that
+ * touches this handle's device state first makes it leave (one stream synchronise), and a device-wide synchronisation
+ * issued elsewhere in the process (cudaDeviceSynchronize, cudaFree, cudaMalloc) waits up to idle_us for it.
+ * idle_us = 0 turns it off.  Zero-copy host path only (n_envs <= 65536), IK-teleport mode. */
+int armsim_host_server(ArmSim* sim, int32_t idle_us);
+
 /* The handle's own pinned (page-locked, device-mapped) I/O block: action f32 [n, act_dim], obs f32 [n, obs_dim],
  * reward f32 [n], done u8 [n], success u8 [n].  Passing exactly these pointers to armsim_step_host makes the call
  * copy-free on the host: for n_envs <= 65536 the kernel reads the actions from and writes the results to this block

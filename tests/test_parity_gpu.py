@@ -624,6 +624,54 @@ def test_full_size_equals_its_shards(pkg, torch_cuda, task, n_total, shard):
         p.close()
 
 
+@pytest.mark.parametrize("task,n", [("reach", 4096), ("push", 1000), ("pick", 130), ("kuka_reach", 33)])
+def test_resident_step_server_equals_launched_host_step(pkg, torch_cuda, task, n):
+    """armsim_host_server: the host step served by ONE resident kernel (command word polled by block 0, relayed to the
+    other blocks, per-block doorbells back) gives bit for bit what the launch-per-step host call gives -- through the
+    synchronous call, the async pair, a state read-back in the middle (the server must leave and come back), an idle
+    period longer than its time-out (it must have left by itself and restart on the next step) and a switch back to the
+    launch path."""
+    import time
+    L = pkg._lib
+    ref = pkg.ArmSimHandle(task, n_envs=n, seed=13, auto_reset=True, max_steps=30)
+    srv = pkg.ArmSimHandle(task, n_envs=n, seed=13, auto_reset=True, max_steps=30)
+    srv.host_server(5000)                                   # 5 ms idle time-out
+    assert np.array_equal(ref.reset_host(), srv.reset_host())
+    rng = np.random.default_rng(13)
+    sc = 0.7 if task in ("reach", "kuka_reach") else 0.4
+
+    def both(a, use_async=False):
+        want = ref.step_host(a)
+        if use_async:
+            srv.host_buffers()[0][:] = a
+            srv.step_async()
+            got = srv.step_wait()
+        else:
+            got = srv.step_host(a)
+        for x, y in zip(want, got):
+            assert np.array_equal(x, y)
+
+    for k in range(60):
+        both(rng.uniform(-sc, sc, (n, 3)).astype(np.float32), use_async=(k % 5 == 4))
+    assert np.array_equal(ref.get_state(L.F_Q), srv.get_state(L.F_Q))          # quiesces the server
+    for k in range(20):
+        both(rng.uniform(-sc, sc, (n, 3)).astype(np.float32))
+    time.sleep(0.05)                                        # 10x the idle time-out: the resident kernel is gone
+    for k in range(20):
+        both(rng.uniform(-sc, sc, (n, 3)).astype(np.float32))
+    srv.host_server(0)                                      # back to launch-per-step
+    for k in range(10):
+        both(rng.uniform(-sc, sc, (n, 3)).astype(np.float32))
+    srv.host_server(5000)
+    both(rng.uniform(-sc, sc, (n, 3)).astype(np.float32))
+    for f in (L.F_Q, L.F_STEP, L.F_EPISODE, L.F_GOAL):
+        assert np.array_equal(ref.get_state(f), srv.get_state(f))
+    assert ref.get_state(L.F_EPISODE).max() >= 3
+    both(rng.uniform(-sc, sc, (n, 3)).astype(np.float32))
+    srv.close()                                             # destroy with the server alive
+    ref.close()
+
+
 @pytest.mark.parametrize("task,ee_z", [("push", 0.02), ("pick", 0.255)])
 def test_squeezed_cubes_multi_wave_equals_single_wave(pkg, oracle, torch_cuda, task, ee_z):
     """The contact solve under load in both builds of the push / pick kernels: with the arm parked low over the cubes -- a
