@@ -467,14 +467,14 @@ step_server_kernel(const __grid_constant__ ChainParams C, const __grid_constant_
         for (unsigned int polls = 0;; ++polls) {
           v = *ctl.cmd;
           if (v == SERVER_STOP || (int)(v - have) > 0) break;
-          if (global_ns() - t0 > ctl.idle_ns || polls > 50000000u) { v = SERVER_STOP; break; }   // (second bound: belt and braces)
+          if ((polls & 15u) == 15u && (global_ns() - t0 > ctl.idle_ns || polls > 50000000u)) { v = SERVER_STOP; break; }   // (second bound: belt and braces)
         }
         *ctl.relay = v;
       } else {
         for (unsigned int polls = 0;; ++polls) {
           v = *ctl.relay;
           if (v == SERVER_STOP || (int)(v - have) > 0) break;
-          if (global_ns() - t0 > 2ull * ctl.idle_ns + 1000000ull || polls > 200000000u) { v = SERVER_STOP; break; }   // (block 0 relays its own time-out first)
+          if ((polls & 63u) == 63u && (global_ns() - t0 > 2ull * ctl.idle_ns + 1000000ull || polls > 200000000u)) { v = SERVER_STOP; break; }   // (block 0 relays its own time-out first)
         }
       }
       s_cmd = v;
