@@ -426,7 +426,7 @@ step_lane_kernel(const __grid_constant__ ChainParams C, const __grid_constant__ 
 
 // The resident form of the host step (armsim_host_server): the same Env.step(), but the kernel stays on the GPU and
 // serves one step per command instead of being launched per step -- a launch-per-step host call spends ~12 of its ~18 us
-// between cudaGraphLaunch and the kernel's first instruction.  Protocol (tools/e2e_breakdown.cu measured the
+// between cudaGraphLaunch and the kernel's first instruction.  Protocol (tools/micro/e2e_breakdown.cu measured the
 // alternatives: 32 blocks polling host memory themselves take 98 us per round trip, one poller + a device relay 7):
 //   host:    writes the actions into the pinned block, then the step's sequence number into the mapped word `cmd`
 //   block 0: thread 0 polls `cmd` over PCIe and republishes it in the device word `relay`; the other blocks poll that

@@ -1,5 +1,5 @@
-// tools/e2e_breakdown.cu -- where the host-buffer step's time goes on this box (measurement tool, not product).
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/e2e_breakdown tools/e2e_breakdown.cu && gpurun_out/e2e_breakdown
+// tools/micro/e2e_breakdown.cu -- where the host-buffer step's time goes on this box (measurement tool, not product).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/e2e_breakdown tools/micro/e2e_breakdown.cu && gpurun_out/e2e_breakdown
 // Each variant: launch -> (PCIe reads) -> (compute stand-in) -> (PCIe writes) -> doorbell in mapped host memory -> host
 // poll.  Prints microseconds per round trip (median of `reps`).
 #include <cuda_runtime.h>
