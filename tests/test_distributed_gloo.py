@@ -48,9 +48,16 @@ def _worker(rank, world, port, out):
     lo, hi = D.shard_range(4097, rank, world)
     stats = D.allreduce_scalars({"succ": float(rank + 1), "n": 1.0})
     flat_w = torch.cat([p.data.reshape(-1) for p in net.parameters()])
-    out.put((rank, flat_w.numpy(), local.numpy(), bucket.flat.numpy().copy(), (lo, hi), stats, bucket.numel))
-    dist.barrier()
-    dist.destroy_process_group()
+    class Holder:                                          # stands in for a VectorTrainer holding recorded collectives
+        released = 0
+
+        def release_graphs(self):
+            Holder.released += 1
+    h = Holder()
+    D.register_graph_holder(h)
+    D.shutdown()                                           # ordered teardown: holders release first, then barrier + destroy
+    out.put((rank, flat_w.numpy(), local.numpy(), bucket.flat.numpy().copy(), (lo, hi), stats, bucket.numel,
+             Holder.released, dist.is_initialized()))
 
 
 def test_gloo_world2_bucket_allreduce_and_sharding():
@@ -65,7 +72,8 @@ def test_gloo_world2_bucket_allreduce_and_sharding():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, w0, l0, g0, s0, st0, n0), (r1, w1, l1, g1, s1, st1, n1) = res
+    assert all(t[7] == 1 and t[8] is False for t in res)   # distributed.shutdown(): graphs released once, group destroyed
+    (r0, w0, l0, g0, s0, st0, n0), (r1, w1, l1, g1, s1, st1, n1) = [t[:7] for t in res]
     assert np.array_equal(w0, w1)                          # replicas stay bit-identical after 3 averaged steps
     assert np.allclose(g0, (l0 + l1) / 2, atol=1e-7) and np.array_equal(g0, g1)   # bucket holds the mean gradient
     assert not np.allclose(l0, l1)
