@@ -21,7 +21,8 @@ K = 2000 measure the same thing to ~1 %; capture_timed_units).  `value` is devic
 synchronize; per rank the MEDIAN interval counts (p10 / p90 are printed too), max over ranks.  `e2e` is the same
 metric through the host-buffer C-ABI call (armsim_step_host on the handle's pinned block: the kernel reads the actions
 from / writes the results to host memory over PCIe every step, the host polls per-block doorbells), timed on the host
-clock as R repeats of a K-step loop, median.
+clock as R repeats of a K-step loop, median -- with the handle's resident step server on (armsim_host_server: one kernel
+stays on the GPU and serves a step per command word) and, beside it as e2e.launch_per_step, with one launch per step.
 Secondary numbers on the same JSON line (single GPU only): other_configs (push / pick / large-N reach, measured the
 same way), rollout_with_td3_actor, e2e.pipelined_depth2 (step_async / step_wait over two env groups).
 """
