@@ -463,14 +463,21 @@ def run_ours(args):
     e2e_times, e2e_incl = launch_times, launch_incl
     if os.environ.get("BENCH_NO_SERVER", "0") != "1" and task in ("reach", "push", "pick", "kuka_reach"):
         srv_times = None
+        ok = 1.0
         try:
             for e in server_group:
                 e.host_server(20000)
-            srv_times, srv_incl = run_e2e(server_group)
         except Exception as ex:      # the launch path stays the number
+            ok = 0.0
             print("resident step server unavailable: %r" % (ex,), file=sys.stderr)
+        if world > 1:                # every rank takes the same legs (run_e2e contains barriers)
+            w = torch.tensor([ok], device=dev, dtype=torch.float64)
+            dist.all_reduce(w, op=dist.ReduceOp.MIN)
+            ok = float(w)
+        if ok > 0.0:
+            srv_times, srv_incl = run_e2e(server_group)
         worse = 1.0 if (srv_times is None or np.median(srv_times) >= np.median(launch_times)) else 0.0
-        if world > 1:                # every rank reports the same mode
+        if world > 1:                # ... and reports the same mode
             w = torch.tensor([worse], device=dev, dtype=torch.float64)
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
             worse = float(w)
