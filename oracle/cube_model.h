@@ -6,7 +6,7 @@
  * This file states the model both the oracle and the CUDA kernels implement instead; the CUDA side
  * (csrc/cube_model.cuh) must match THIS to fp32 tolerance.  System-level pins: the reference's untouched-cube return
  * (-504, visdata/push/updata_TD3) and its push learning curve reproduced by the reference's OWN learner on this model
- * (tests/system/ref_learner_on_oracle.py, tests/golden/ref_learner_push_*.json).
+ * (tests/system/ref_learner_on_oracle.py, tests/golden/ref_learner_{reach,push,pick}_*.json, tests/test_system_pins.py).
  *
  * Model, per sim step, with Bullet's / pybullet's default parameters:
  *   dt 1/240 s, gravity (0,0,-10), ERP 0.2 applied as a velocity bias (btMultiBody contacts have no split impulse),

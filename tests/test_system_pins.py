@@ -44,3 +44,16 @@ def test_reference_learner_pushes_on_the_oracle():
     first_half = next(i for i, r in enumerate(rates) if r >= 0.5)
     assert (first_half + 1) * 25 <= 700                                  # reference: 0.52 at 600 episodes
     assert max(rates) >= 0.7 and np.mean(rates[-8:]) >= 0.55
+
+
+def test_reference_learner_second_seed_and_pick():
+    """push seed 1: the same plateau-then-jump as the reference's run, later (0.5 after 1150 episodes, 0.84 after 1475);
+    pick + DATD3 (BASELINE config 4; no curve ships with the reference): the friction-only grasp is learnable -- the cube
+    is carried to within 5 cm of airborne targets in 30-48 % of the episodes after 600"""
+    d = _load("ref_learner_push_TD3_seed1.json")
+    rates, ret = d["success_rate_per_25"], np.array(d["returns"])
+    assert max(rates[:40]) <= 0.3 and max(rates[-8:]) >= 0.8 and 110.0 <= ret.max() <= 125.0
+    d = _load("ref_learner_pick_DATD3.json")
+    rates, ret = d["success_rate_per_25"], np.array(d["returns"])
+    assert d["algo"] == "DATD3_MLP" and np.mean(rates[-16:]) >= 0.25 and max(rates) >= 0.4
+    assert -520.0 <= ret[:5].min() and ret[:5].max() <= -300.0 and 110.0 <= ret.max() <= 125.0
