@@ -16,7 +16,10 @@
  *     link's INERTIAL frame: 2 cm up the local z axis for link 7.  If so, Bullet's linear rows
  *     differ by omega x (0.02 m lever): another iterate path and sometimes another iteration count, but the same
  *     stopping rule on the link-frame position, i.e. the same end point to within the 1e-4 m residual.  Nothing
- *     downstream of the step (obs, reward, done) sees more than that.
+ *     downstream of the step (obs, reward, done) sees more than that.  Measured (tools/ik_reference_point_study.py,
+ *     1500 servo moves of the reach workspace, both Jacobians from the same start): end points differ by 2.9e-6 m at
+ *     the median, 4.7e-5 m at the 99th percentile, 1.0e-4 m at most; same iteration count in 99.8 % of the moves
+ *     (profiles/r02_ik_reference_point_study.json).
  *   - Orientation error is formed as 2 atan2(|v|, w) v/|v| instead of 2 acos(w) v/sqrt(1-w^2): the same value for a
  *     unit quaternion, better conditioned near zero.
  *   - An iteration that does not converge within 20 updates (targets clipped to an unreachable workspace corner, or
