@@ -53,6 +53,11 @@ def test_reference_learner_second_seed_and_pick():
     d = _load("ref_learner_push_TD3_seed1.json")
     rates, ret = d["success_rate_per_25"], np.array(d["returns"])
     assert max(rates[:40]) <= 0.3 and max(rates[-8:]) >= 0.8 and 110.0 <= ret.max() <= 125.0
+    for name, best in (("ref_learner_push_TD3_seed2.json", 0.9), ("ref_learner_push_TD3_seed3.json", 0.8)):
+        d = _load(name)
+        rates, ret = d["success_rate_per_25"], np.array(d["returns"])
+        first_half = next(i for i, r in enumerate(rates) if r >= 0.5)
+        assert 600 <= (first_half + 1) * 25 <= 900 and max(rates) >= best and 110.0 <= ret.max() <= 125.0
     d = _load("ref_learner_pick_DATD3.json")
     rates, ret = d["success_rate_per_25"], np.array(d["returns"])
     assert d["algo"] == "DATD3_MLP" and np.mean(rates[-16:]) >= 0.25 and max(rates) >= 0.4
