@@ -37,7 +37,10 @@ class OracleEnv:
 
     def __init__(self, task, seed=0):
         self.task = task
-        self.sim = O.OracleSim(O.default_config(TASKS[task], 1, seed=seed, auto_reset=0))
+        kw = {}
+        if os.environ.get("REACH_DIS"):          # the reference's "harder" reach runs: opt.reach_dis = 0.005 (visdata/reach/*_0.005)
+            kw["reach_dis"] = float(os.environ["REACH_DIS"])
+        self.sim = O.OracleSim(O.default_config(TASKS[task], 1, seed=seed, auto_reset=0, **kw))
 
     def reset(self):
         return self.sim.reset()[0].astype(np.float64)

@@ -30,6 +30,17 @@ def test_reference_learner_reaches_on_the_oracle():
     assert -3800.0 <= ret[:5].min() and ret[:5].max() <= -100.0
 
 
+def test_reference_ddpg_and_harder_reach_on_the_oracle():
+    """reach + DDPG (visdata/reach/DDPG_0.01: 0.92 after 100 episodes, 1.0 in the last 5 windows, avg return -62 .. -84) and
+    the 'harder' run with opt.reach_dis = 0.005 (visdata/reach/TD3_0.005: avg return -113 .. -161 at the end)"""
+    d = _load("ref_learner_reach_DDPG.json")
+    rates, ret = d["success_rate_per_25"], np.array(d["returns"])
+    assert d["algo"] == "DDPG_MLP" and min(rates[-5:]) == 1.0 and rates[3] >= 0.9 and -90.0 <= ret[-125:].mean() <= -50.0
+    d = _load("ref_learner_reach_TD3_harder.json")
+    rates, ret = d["success_rate_per_25"], np.array(d["returns"])
+    assert len(ret) == 2250 and np.mean(rates[-20:]) >= 0.6 and -170.0 <= ret[-250:].mean() <= -100.0
+
+
 def test_reference_learner_pushes_on_the_oracle():
     """push + TD3: visdata/push/updata_TD3 (5000 episodes): first returns -368, -320, -436, -504, -481; best return +118.97;
     success 0.24 / 0.16 / 0.40 / 0.52 after 150 / 300 / 450 / 600 episodes, 0.96 after 750.  On the oracle (seed 0): the
