@@ -76,7 +76,7 @@ def lib():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if os.environ.get("ARMSIM_LIB"):         # A/B experiments: another build of the SAME ABI (tools/ab_build.sh)
+    if os.environ.get("ARMSIM_LIB"):         # A/B experiments: another build of the SAME ABI (nvcc ... -D<variant> -o <path>)
         path = os.environ["ARMSIM_LIB"]
     elif not os.path.exists(path) or (_build.needs_build() and os.environ.get("ARMSIM_AUTO_REBUILD", "1") != "0"):
         path = _build.build_libarmsim()      # missing, or older than csrc/ / include/: never load a stale library
