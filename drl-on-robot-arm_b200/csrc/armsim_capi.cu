@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "armsim.h"
@@ -207,13 +209,18 @@ static bool pdl_enabled() {
 template <class F>
 static void ensure_smem(F kern, size_t bytes) {
   // static + dynamic shared memory above 48 KB needs the opt-in even when the dynamic part alone is below it (torque
-  // kernels: 12 KB static staging + 41.5 KB contact slots), so every kernel with contact slots opts in -- once
+  // kernels: 12 KB static staging + 41.5 KB contact slots), so every kernel with contact slots opts in -- once per
+  // device (the attribute belongs to the function on the CURRENT device) and safely from several host threads
   if (bytes == 0) return;
-  static std::vector<const void*> done;
-  for (const void* p : done)
-    if (p == (const void*)kern) return;
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& p : done)
+    if (p.first == (const void*)kern && p.second == dev) return;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  done.push_back((const void*)kern);
+  done.emplace_back((const void*)kern, dev);
 }
 
 template <class... KArgs, class... Args>
