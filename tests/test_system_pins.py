@@ -69,6 +69,9 @@ def test_reference_learner_second_seed_and_pick():
         rates, ret = d["success_rate_per_25"], np.array(d["returns"])
         first_half = next(i for i, r in enumerate(rates) if r >= 0.5)
         assert 600 <= (first_half + 1) * 25 <= 900 and max(rates) >= best and 110.0 <= ret.max() <= 125.0
+    d = _load("ref_learner_push_TD3_long.json")                         # 2500 episodes: the reference's final level is reached
+    rates = d["success_rate_per_25"]
+    assert len(d["returns"]) == 2500 and max(rates[-12:]) >= 0.9 and np.mean(rates[-12:]) >= 0.75
     d = _load("ref_learner_pick_DATD3.json")
     rates, ret = d["success_rate_per_25"], np.array(d["returns"])
     assert d["algo"] == "DATD3_MLP" and np.mean(rates[-16:]) >= 0.25 and max(rates) >= 0.4
