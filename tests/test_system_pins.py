@@ -75,6 +75,8 @@ def test_reference_learner_second_seed_and_pick():
     d = _load("ref_learner_pick_DATD3.json")
     rates, ret = d["success_rate_per_25"], np.array(d["returns"])
     assert d["algo"] == "DATD3_MLP" and np.mean(rates[-16:]) >= 0.25 and max(rates) >= 0.4
+    lng = _load("ref_learner_pick_DATD3_long.json")                     # 3000 episodes, seed 1
+    assert len(lng["returns"]) == 3000 and np.mean(lng["success_rate_per_25"][-20:]) >= 0.5 and max(lng["success_rate_per_25"]) >= 0.75
     t = _load("ref_learner_pick_TD3.json")                               # main.py:518-584 trains pick with TD3
     assert t["algo"] == "TD3_MLP" and np.mean(t["success_rate_per_25"][-16:]) >= 0.3 and 110.0 <= max(t["returns"]) <= 125.0
     assert -520.0 <= ret[:5].min() and ret[:5].max() <= -300.0 and 110.0 <= ret.max() <= 125.0
